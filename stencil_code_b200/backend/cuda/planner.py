@@ -1,0 +1,71 @@
+"""Tiling / launch-geometry planner of the CUDA backend.
+
+Replaces reference ``backend/local_size_computer.py:17-253`` (the OpenCL work-group shape
+chooser) and the global-size logic of ``backend/ocl_boundary_copier.py:69-84``.  Like the
+reference's planner it is pure host arithmetic over a device-properties record, so it can be
+unit-tested with a fake device (the reference does that with ``MockDevice``,
+``test/fixtures.py:3-11``); unlike it, it chooses between code-generation strategies:
+
+  direct  one thread per point, global loads (``codegen_direct``) -- any shape / dtype / rank
+  stream  TMA-staged shared-memory tiles streamed along axis 0 with a register window
+          (``codegen_stream``) -- float32 grids of rank 2 or 3 whose rows are 16-byte multiples
+"""
+from ...stencil_exception import StencilException
+from . import codegen_direct
+
+
+class DeviceProps(object):
+    """The few device facts the planner uses; defaults describe a B200 (sm_100a)."""
+    def __init__(self, sm_count=148, smem_per_sm=233472, smem_per_block_optin=232448,
+                 regs_per_sm=65536, max_threads_per_sm=2048, l2_bytes=126 * 1024 * 1024,
+                 name="NVIDIA B200"):
+        self.sm_count = sm_count
+        self.smem_per_sm = smem_per_sm
+        self.smem_per_block_optin = smem_per_block_optin
+        self.regs_per_sm = regs_per_sm
+        self.max_threads_per_sm = max_threads_per_sm
+        self.l2_bytes = l2_bytes
+        self.name = name
+
+
+B200 = DeviceProps()
+
+
+class Launch(object):
+    def __init__(self, grid, block, smem=0, cluster=(1, 1, 1)):
+        self.grid, self.block, self.smem, self.cluster = tuple(grid), tuple(block), int(smem), tuple(cluster)
+
+
+def plan(program, domain, device_props=None, forced_strategy=None, options=()):
+    from .transformer import CudaPlan
+    device_props = device_props or B200
+    strategy = forced_strategy
+    reason = "forced" if forced_strategy else None
+    if strategy is None:
+        from . import codegen_stream
+        ok, reason = codegen_stream.applicable(program, domain, device_props)
+        strategy = 'stream' if ok else 'direct'
+    if strategy == 'stream':
+        from . import codegen_stream
+        ok, why = codegen_stream.applicable(program, domain, device_props)
+        if not ok:
+            raise StencilException("strategy 'stream' cannot handle this stencil: " + why)
+        return codegen_stream.make_plan(program, domain, device_props, options)
+    if strategy != 'direct':
+        raise StencilException("unknown strategy '{}'".format(strategy))
+    source = codegen_direct.generate(program, domain)
+
+    def geometry(a0_begin, a0_end):
+        grid, block = codegen_direct.launch_geometry(program, a0_begin, a0_end)
+        return Launch(grid, block)
+
+    return CudaPlan(program, domain, 'direct', source, 'stencil_direct', options, geometry,
+                    notes={'why': reason})
+
+
+def halo_slabs(shape, ghost_depth):
+    """The disjoint slab cover of the halo shell used by ``HaloEnumerator`` as index ranges --
+    the device-side decomposition that replaces one OpenCL boundary kernel per dimension
+    (reference ``backend/ocl_boundary_copier.py:69-84``)."""
+    from ...halo_enumerator import HaloEnumerator
+    return [tuple((r.start, r.stop) for r in slab) for slab in HaloEnumerator(ghost_depth, shape).slabs()]

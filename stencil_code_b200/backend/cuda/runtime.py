@@ -1,0 +1,498 @@
+"""Host runtime of the CUDA backend: ctypes binding of the C-ABI shim and the concrete callable.
+
+Replaces reference ``ConcreteStencil`` / ``OclStencilFunction`` (``stencil_kernel.py:61-208``):
+``ConcreteCudaStencil.__call__`` is what ``Stencil.__call__`` ends up in.  numpy arrays go
+host -> device -> kernel -> host (what ``OclStencilFunction.__call__`` does with pycl buffers,
+``:162-202``); torch CUDA tensors are used in place and a CUDA tensor is returned (the analogue of
+the reference's device-resident ``hmarray`` path, ``:153-165,197-198``).
+
+There is no fallback: if ``libstencil_cuda.so`` or a GPU is missing the call raises
+``StencilException``.
+"""
+import atexit
+import ctypes
+import os
+import threading
+import weakref
+
+import numpy
+
+from ...stencil_exception import StencilException
+
+_CSRC = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "csrc"))
+LIBRARY_PATH = os.path.join(_CSRC, "libstencil_cuda.so")
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class ScTmap(ctypes.Structure):
+    _fields_ = [("opaque", ctypes.c_uint64 * 16)]
+    _align_ = 64
+
+
+class ScDeviceProps(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 128),
+                ("cc_major", ctypes.c_int32), ("cc_minor", ctypes.c_int32),
+                ("sm_count", ctypes.c_int32), ("max_threads_per_block", ctypes.c_int32),
+                ("max_threads_per_sm", ctypes.c_int32), ("regs_per_sm", ctypes.c_int32),
+                ("smem_per_sm", ctypes.c_int32), ("smem_per_block_optin", ctypes.c_int32),
+                ("l2_bytes", ctypes.c_int32), ("sm_clock_khz", ctypes.c_int32),
+                ("mem_clock_khz", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4),
+                ("total_mem", ctypes.c_uint64)]
+
+
+# name -> (restype, argtypes); every symbol include/stencil_cuda.h declares
+_VP, _I, _SZ = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+_PVP = ctypes.POINTER(ctypes.c_void_p)
+_U32x3 = ctypes.POINTER(ctypes.c_uint32)
+SYMBOLS = {
+    "sc_abi_version": (_I, []),
+    "sc_last_error": (ctypes.c_char_p, []),
+    "sc_driver_available": (_I, []),
+    "sc_device_count": (_I, [ctypes.POINTER(_I)]),
+    "sc_init": (_I, [_I]),
+    "sc_set_device": (_I, [_I]),
+    "sc_get_device": (_I, [ctypes.POINTER(_I)]),
+    "sc_device_props_get": (_I, [_I, ctypes.POINTER(ScDeviceProps)]),
+    "sc_mem_info": (_I, [ctypes.POINTER(_SZ), ctypes.POINTER(_SZ)]),
+    "sc_device_synchronize": (_I, []),
+    "sc_compile": (_I, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), _I, _PVP]),
+    "sc_module_from_cubin": (_I, [_VP, _SZ, _PVP]),
+    "sc_module_load": (_I, [_VP]),
+    "sc_module_cubin": (_I, [_VP, _PVP, ctypes.POINTER(_SZ)]),
+    "sc_module_log": (ctypes.c_char_p, [_VP]),
+    "sc_module_free": (_I, [_VP]),
+    "sc_function_info": (_I, [_VP, ctypes.c_char_p] + [ctypes.POINTER(_I)] * 4),
+    "sc_function_occupancy": (_I, [_VP, ctypes.c_char_p, _I, _SZ, ctypes.POINTER(_I)]),
+    "sc_tensormap_tiled": (_I, [ctypes.POINTER(ScTmap), _VP, _I, _I, ctypes.POINTER(ctypes.c_uint64),
+                                ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), _I]),
+    "sc_launch": (_I, [_VP, ctypes.c_char_p, _U32x3, _U32x3, _U32x3, ctypes.c_uint32, _VP, _PVP]),
+    "sc_stream_create": (_I, [_PVP]),
+    "sc_stream_destroy": (_I, [_VP]),
+    "sc_stream_synchronize": (_I, [_VP]),
+    "sc_stream_wait_event": (_I, [_VP, _VP]),
+    "sc_event_create": (_I, [_PVP, _I]),
+    "sc_event_create_ipc": (_I, [_PVP]),
+    "sc_event_destroy": (_I, [_VP]),
+    "sc_event_record": (_I, [_VP, _VP]),
+    "sc_event_synchronize": (_I, [_VP]),
+    "sc_event_elapsed_ms": (_I, [_VP, _VP, ctypes.POINTER(ctypes.c_float)]),
+    "sc_malloc": (_I, [_PVP, _SZ]),
+    "sc_free": (_I, [_VP]),
+    "sc_memset32_async": (_I, [_VP, ctypes.c_uint32, _SZ, _VP]),
+    "sc_memcpy_h2d_async": (_I, [_VP, _VP, _SZ, _VP]),
+    "sc_memcpy_d2h_async": (_I, [_VP, _VP, _SZ, _VP]),
+    "sc_memcpy_d2d_async": (_I, [_VP, _VP, _SZ, _VP]),
+    "sc_host_alloc": (_I, [_PVP, _SZ]),
+    "sc_host_free": (_I, [_VP]),
+    "sc_host_register": (_I, [_VP, _SZ]),
+    "sc_host_unregister": (_I, [_VP]),
+    "sc_ipc_get_mem_handle": (_I, [_VP, ctypes.c_char_p]),
+    "sc_ipc_open_mem_handle": (_I, [ctypes.c_char_p, _PVP]),
+    "sc_ipc_close_mem_handle": (_I, [_VP]),
+    "sc_ipc_get_event_handle": (_I, [_VP, ctypes.c_char_p]),
+    "sc_ipc_open_event_handle": (_I, [ctypes.c_char_p, _PVP]),
+}
+
+
+def load_library():
+    """The shim, loaded once.  Raises StencilException when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIBRARY_PATH):
+                raise StencilException(
+                    "the CUDA shim {} is missing; build it with `make -C {}` (or "
+                    "`python -c 'import __graft_entry__ as g; g.build()'`)".format(LIBRARY_PATH, _CSRC))
+            library = ctypes.CDLL(LIBRARY_PATH)
+            for name, (restype, argtypes) in SYMBOLS.items():
+                function = getattr(library, name)
+                function.restype = restype
+                function.argtypes = argtypes
+            if library.sc_abi_version() != 1:
+                raise StencilException("libstencil_cuda.so has ABI version {}, expected 1".format(
+                    library.sc_abi_version()))
+            _lib = library
+    return _lib
+
+
+def check(code, what=""):
+    if code != 0:
+        message = load_library().sc_last_error().decode(errors="replace")
+        raise StencilException("CUDA backend error{}: {}".format(
+            " in " + what if what else "", message or "code {}".format(code)))
+
+
+# ---- modules -------------------------------------------------------------------------------------
+class Module(object):
+    def __init__(self, handle, name):
+        self.handle = handle
+        self.name = name
+        self._keepalive = []
+
+    def cubin(self):
+        data, size = ctypes.c_void_p(), ctypes.c_size_t()
+        check(load_library().sc_module_cubin(self.handle, ctypes.byref(data), ctypes.byref(size)))
+        return ctypes.string_at(data, size.value)
+
+    def log(self):
+        return load_library().sc_module_log(self.handle).decode(errors="replace")
+
+    def load(self):
+        check(load_library().sc_module_load(self.handle), "module load")
+
+    def function_info(self, function):
+        values = [ctypes.c_int() for _ in range(4)]
+        check(load_library().sc_function_info(self.handle, function.encode(),
+                                              *[ctypes.byref(v) for v in values]))
+        return dict(zip(("regs", "static_smem", "local_bytes", "max_threads"),
+                        (v.value for v in values)))
+
+    def occupancy(self, function, block_threads, dynamic_smem):
+        blocks = ctypes.c_int()
+        check(load_library().sc_function_occupancy(self.handle, function.encode(), block_threads,
+                                                   dynamic_smem, ctypes.byref(blocks)))
+        return blocks.value
+
+
+def compile_source(source, name="stencil_kernel.cu", options=()):
+    """NVRTC-compile CUDA C++ for sm_100a (works without a GPU; the shim caches by source)."""
+    library = load_library()
+    raw = (ctypes.c_char_p * len(options))(*[o.encode() for o in options])
+    handle = ctypes.c_void_p()
+    check(library.sc_compile(source.encode(), name.encode(), raw, len(options), ctypes.byref(handle)),
+          "JIT compile of " + name)
+    return Module(handle, name)
+
+
+def module_from_cubin(data, name="cubin"):
+    handle = ctypes.c_void_p()
+    buffer = ctypes.create_string_buffer(data, len(data))
+    check(load_library().sc_module_from_cubin(buffer, len(data), ctypes.byref(handle)))
+    return Module(handle, name)
+
+
+# ---- devices ---------------------------------------------------------------------------------------
+class Device(object):
+    """One initialised GPU: properties, a compute stream, two copy streams, buffer caches."""
+    _instances = {}
+    _lock = threading.Lock()
+
+    def __init__(self, index):
+        library = load_library()
+        if not library.sc_driver_available():
+            check(library.sc_init(index), "device initialisation")      # raises with the reason
+        check(library.sc_init(index), "device initialisation")
+        self.index = index
+        props = ScDeviceProps()
+        check(library.sc_device_props_get(index, ctypes.byref(props)))
+        self.props = props
+        self.name = props.name.decode()
+        self.stream = self._new_stream()
+        self.h2d_stream = self._new_stream()
+        self.d2h_stream = self._new_stream()
+        self._free_device = {}       # nbytes -> [ptr]
+        self._free_pinned = {}       # nbytes -> [ptr]
+        self._utils = None
+
+    @classmethod
+    def get(cls, index=None):
+        if index is None:
+            index = int(os.environ.get("STENCIL_CUDA_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        with cls._lock:
+            device = cls._instances.get(index)
+            if device is None:
+                device = cls(index)
+                cls._instances[index] = device
+        check(load_library().sc_set_device(index))
+        return device
+
+    def planner_props(self):
+        from .planner import DeviceProps
+        p = self.props
+        return DeviceProps(sm_count=p.sm_count, smem_per_sm=p.smem_per_sm,
+                           smem_per_block_optin=p.smem_per_block_optin, regs_per_sm=p.regs_per_sm,
+                           max_threads_per_sm=p.max_threads_per_sm, l2_bytes=p.l2_bytes,
+                           name=self.name)
+
+    # -- streams / events
+    def _new_stream(self):
+        stream = ctypes.c_void_p()
+        check(load_library().sc_stream_create(ctypes.byref(stream)))
+        return stream
+
+    def new_event(self, timing=False):
+        event = ctypes.c_void_p()
+        check(load_library().sc_event_create(ctypes.byref(event), 1 if timing else 0))
+        return event
+
+    def synchronize(self, stream=None):
+        if stream is None:
+            check(load_library().sc_device_synchronize())
+        else:
+            check(load_library().sc_stream_synchronize(stream))
+
+    # -- device memory (size-keyed free lists: a call's buffers are reused by the next call)
+    def alloc(self, nbytes):
+        nbytes = max(256, (int(nbytes) + 255) // 256 * 256)
+        bucket = self._free_device.get(nbytes)
+        if bucket:
+            return DeviceBuffer(self, bucket.pop(), nbytes)
+        pointer = ctypes.c_void_p()
+        code = load_library().sc_malloc(ctypes.byref(pointer), nbytes)
+        if code != 0:
+            self.trim()
+            check(load_library().sc_malloc(ctypes.byref(pointer), nbytes), "device allocation")
+        return DeviceBuffer(self, pointer.value, nbytes)
+
+    def _release(self, pointer, nbytes):
+        self._free_device.setdefault(nbytes, []).append(pointer)
+
+    def trim(self):
+        """Return every cached device / pinned block to the driver."""
+        library = load_library()
+        for bucket in self._free_device.values():
+            while bucket:
+                library.sc_free(ctypes.c_void_p(bucket.pop()))
+        for bucket in self._free_pinned.values():
+            while bucket:
+                library.sc_host_free(ctypes.c_void_p(bucket.pop()))
+
+    # -- pinned host memory
+    def pinned_empty(self, shape, dtype):
+        """numpy array in page-locked memory; the block returns to a pool when the array dies."""
+        dtype = numpy.dtype(dtype)
+        count = int(numpy.prod(shape, dtype=numpy.int64)) if len(shape) else 1
+        nbytes = max(4096, (count * dtype.itemsize + 4095) // 4096 * 4096)
+        bucket = self._free_pinned.get(nbytes)
+        if bucket:
+            pointer = bucket.pop()
+        else:
+            raw = ctypes.c_void_p()
+            check(load_library().sc_host_alloc(ctypes.byref(raw), nbytes), "pinned allocation")
+            pointer = raw.value
+        block = (ctypes.c_char * nbytes).from_address(pointer)
+        array = numpy.frombuffer(block, dtype=dtype, count=count).reshape(shape)
+        weakref.finalize(block, self._free_pinned.setdefault(nbytes, []).append, pointer)
+        _PINNED_RANGES.append((pointer, pointer + nbytes))
+        return array
+
+    # -- helper kernels (csrc/device_utils.cu)
+    def utils(self):
+        if self._utils is None:
+            cubin_path = os.path.join(_CSRC, "device_utils.cubin")
+            if os.path.exists(cubin_path):
+                with open(cubin_path, "rb") as handle:
+                    self._utils = module_from_cubin(handle.read(), "device_utils")
+            else:
+                with open(os.path.join(_CSRC, "device_utils.cu")) as handle:
+                    self._utils = compile_source(handle.read(), "device_utils.cu", ("-lineinfo",))
+            self._utils.load()
+        return self._utils
+
+
+_PINNED_RANGES = []
+
+
+def is_pinned(array):
+    address = array.ctypes.data
+    return any(lo <= address < hi for lo, hi in _PINNED_RANGES)
+
+
+class DeviceBuffer(object):
+    """A device allocation that goes back to its device's free list when dropped."""
+    def __init__(self, device, pointer, nbytes):
+        self.device, self.ptr, self.nbytes = device, pointer, nbytes
+        self._finalizer = weakref.finalize(self, device._release, pointer, nbytes)
+
+    def release(self):
+        self._finalizer()
+
+
+@atexit.register
+def _shutdown():
+    for device in list(Device._instances.values()):
+        try:
+            load_library().sc_set_device(device.index)
+            device.trim()
+        except Exception:
+            pass
+
+
+def launch(module, function, launch_cfg, args, stream):
+    """args: list of ctypes objects (by value); marshalled as an array of pointers to them."""
+    library = load_library()
+    pointers = (ctypes.c_void_p * len(args))(*[ctypes.cast(ctypes.byref(a), ctypes.c_void_p) for a in args])
+    grid = (ctypes.c_uint32 * 3)(*launch_cfg.grid)
+    block = (ctypes.c_uint32 * 3)(*launch_cfg.block)
+    cluster = (ctypes.c_uint32 * 3)(*launch_cfg.cluster)
+    check(library.sc_launch(module.handle, function.encode(), grid, block, cluster,
+                            launch_cfg.smem, stream, pointers), "launch of " + function)
+
+
+# ---- the concrete callable ----------------------------------------------------------------------
+def _is_torch_tensor(obj):
+    return hasattr(obj, "data_ptr") and hasattr(obj, "is_cuda")
+
+
+class ConcreteCudaStencil(object):
+    """A compiled, launchable specialisation (what ``SpecializedStencil.finalize`` returns)."""
+
+    def __init__(self, plan, device_index=None):
+        self.plan = plan
+        self.program = plan.program
+        self.device = Device.get(device_index)
+        self.module = compile_source(plan.source, "stencil_{}.cu".format(plan.strategy), plan.options)
+        self.module.load()
+        self._tmaps = {}
+        self.last_kernel_ms = None
+
+    # -- argument checks (the reference's ndpointer argtypes raise TypeError on mismatch)
+    def _check_args(self, args):
+        program = self.program
+        if len(args) != len(program.args):
+            raise StencilException("stencil takes {} arguments, got {}".format(len(program.args), len(args)))
+        for info, arg in zip(program.args, args):
+            shape = tuple(int(s) for s in arg.shape)
+            dtype = numpy.dtype(str(arg.dtype).replace("torch.", "")) if _is_torch_tensor(arg) \
+                else numpy.dtype(arg.dtype)
+            if shape != info.shape or dtype != info.dtype:
+                raise TypeError("argument '{}' must have shape {} and dtype {}, got {} {}".format(
+                    info.name, info.shape, info.dtype, shape, dtype))
+
+    def _tensor_map(self, spec, pointer):
+        key = (spec.key, pointer)
+        tmap = self._tmaps.get(key)
+        if tmap is None:
+            tmap = ScTmap()
+            rank = len(spec.dims)
+            dims = (ctypes.c_uint64 * rank)(*spec.dims)
+            strides = (ctypes.c_uint64 * max(1, rank - 1))(*spec.strides_bytes)
+            box = (ctypes.c_uint32 * rank)(*spec.box)
+            check(load_library().sc_tensormap_tiled(ctypes.byref(tmap), ctypes.c_void_p(pointer),
+                                                    spec.dtype_code, rank, dims, strides, box, 0),
+                  "tensor map encode")
+            if len(self._tmaps) > 64:
+                self._tmaps.clear()
+            self._tmaps[key] = tmap
+        return tmap
+
+    def launch(self, arg_pointers, out_pointer, a0_begin=None, a0_end=None, stream=None):
+        """Enqueue the stencil over axis-0 range [a0_begin, a0_end) on ``stream``."""
+        plan = self.plan
+        lo, hi = plan.domain.sweep_range
+        a0_begin = lo if a0_begin is None else a0_begin
+        a0_end = hi if a0_end is None else a0_end
+        if a0_end <= a0_begin:
+            return
+        values = []
+        for info, pointer in zip(self.program.args, arg_pointers):
+            values.append(ctypes.c_void_p(pointer))
+        for spec in plan.tensor_maps:
+            values.append(self._tensor_map(spec, arg_pointers[spec.arg]))
+        values.append(ctypes.c_void_p(out_pointer))
+        values.append(ctypes.c_int(a0_begin))
+        values.append(ctypes.c_int(a0_end))
+        launch(self.module, plan.function, plan.geometry(a0_begin, a0_end), values,
+               self.device.stream if stream is None else stream)
+
+    # -- the call --------------------------------------------------------------------------------
+    def __call__(self, *args, **kwargs):
+        out = kwargs.pop("out", None)
+        if kwargs:
+            raise StencilException("unexpected keyword arguments {}".format(sorted(kwargs)))
+        self._check_args(args)
+        if _is_torch_tensor(args[0]):
+            return self._call_torch(args, out)
+        return self._call_numpy(args, out)
+
+    def _call_torch(self, args, out):
+        import torch
+        grid = args[0]
+        if not grid.is_cuda:
+            raise StencilException("torch tensors must live on a CUDA device (numpy arrays are "
+                                   "copied for you)")
+        if grid.device.index != self.device.index:
+            raise StencilException("tensor is on cuda:{} but the stencil was specialised on cuda:{}"
+                                   .format(grid.device.index, self.device.index))
+        tensors = []
+        for arg in args:
+            tensor = arg if _is_torch_tensor(arg) else torch.as_tensor(arg)
+            tensors.append(tensor.to(grid.device).contiguous())
+        result = torch.empty_like(tensors[0]) if out is None else out
+        if not result.is_contiguous():
+            raise StencilException("out= must be contiguous")
+        stream = ctypes.c_void_p(torch.cuda.current_stream(grid.device).cuda_stream)
+        self.launch([t.data_ptr() for t in tensors], result.data_ptr(), stream=stream)
+        return result
+
+    def _call_numpy(self, args, out):
+        library = load_library()
+        device = self.device
+        check(library.sc_set_device(device.index))
+        stream = device.stream
+        arrays = [numpy.ascontiguousarray(a) for a in args]
+        buffers = [device.alloc(a.nbytes) for a in arrays]
+        out_buffer = device.alloc(arrays[0].nbytes)
+        for array, buffer in zip(arrays, buffers):
+            check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(array.ctypes.data),
+                                              array.nbytes, stream))
+        self.launch([b.ptr for b in buffers], out_buffer.ptr, stream=stream)
+        if out is None:
+            result = device.pinned_empty(arrays[0].shape, arrays[0].dtype)
+        else:
+            if out.shape != arrays[0].shape or out.dtype != arrays[0].dtype or not out.flags.c_contiguous:
+                raise StencilException("out= must be a C-contiguous array of the grid's shape and dtype")
+            result = out
+        check(library.sc_memcpy_d2h_async(ctypes.c_void_p(result.ctypes.data), ctypes.c_void_p(out_buffer.ptr),
+                                          result.nbytes, stream))
+        device.synchronize(stream)
+        for buffer in buffers + [out_buffer]:
+            buffer.release()
+        return result
+
+    # -- iterated application -------------------------------------------------------------------
+    def iterate(self, grid, iterations, *tables, **kwargs):
+        """``iterations`` sweeps ``g = stencil(g, *tables)`` with the grid resident on the device
+        (ping-pong between two buffers); bit-identical to calling the stencil in a loop."""
+        if iterations < 0:
+            raise StencilException("iterations must be >= 0")
+        args = (grid,) + tuple(tables)
+        self._check_args(args)
+        library = load_library()
+        device = self.device
+        if _is_torch_tensor(grid):
+            import torch
+            stream = ctypes.c_void_p(torch.cuda.current_stream(grid.device).cuda_stream)
+            tensors = [t.contiguous() for t in args]
+            current = tensors[0]
+            spare = torch.empty_like(current)
+            result = None
+            for _ in range(iterations):
+                self.launch([current.data_ptr()] + [t.data_ptr() for t in tensors[1:]],
+                            spare.data_ptr(), stream=stream)
+                current, spare = spare, (current if current is not tensors[0] else torch.empty_like(current))
+                result = current
+            return grid.clone() if result is None else result
+        check(library.sc_set_device(device.index))
+        stream = device.stream
+        arrays = [numpy.ascontiguousarray(a) for a in args]
+        buffers = [device.alloc(a.nbytes) for a in arrays]
+        spare = device.alloc(arrays[0].nbytes)
+        for array, buffer in zip(arrays, buffers):
+            check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(array.ctypes.data),
+                                              array.nbytes, stream))
+        current = buffers[0]
+        for _ in range(iterations):
+            self.launch([current.ptr] + [b.ptr for b in buffers[1:]], spare.ptr, stream=stream)
+            current, spare = spare, current
+        result = device.pinned_empty(arrays[0].shape, arrays[0].dtype)
+        check(library.sc_memcpy_d2h_async(ctypes.c_void_p(result.ctypes.data), ctypes.c_void_p(current.ptr),
+                                          result.nbytes, stream))
+        device.synchronize(stream)
+        for buffer in buffers[1:] + [current, spare]:
+            buffer.release()
+        return result

@@ -1,0 +1,273 @@
+"""The public stencil API: subclass ``Stencil``, define ``neighborhoods`` and ``kernel``, call it.
+
+Same surface as reference ``stencil_code/stencil_kernel.py:449-664`` -- constructor keywords,
+``__call__``, ``interior_points``, ``neighbors``, ``halo_points``, ``interior_points_slice``,
+``distance``, ``constants``, ``clamp``, ``compute_ghost_depth`` and the exception messages the
+reference's tests look for -- with one executable specialising backend, ``'cuda'`` (the default;
+the reference's default ``'ocl'`` and its ``'c'``/``'omp'`` need ctree/pycl, which this build
+neither has nor wants: asking for them raises).  ``backend='python'`` remains the literal
+interpreter of ``kernel`` (reference ``:545-559``); it is only ever chosen explicitly, it is not a
+fallback for anything.
+
+``SpecializedStencil`` is the JIT driver that replaces the ctree ``LazySpecializedFunction`` of
+reference ``:216-416``: same cache key (``args_to_subconfig``, ``:244-256``), same
+transform -> finalize -> concrete-function life cycle, NVRTC instead of gcc.  Constructing a
+``Stencil`` never touches a device (reference section 3.1 of SURVEY.md).
+"""
+from __future__ import print_function
+
+import abc
+import itertools
+import math
+from collections import namedtuple
+
+import numpy as np
+
+from .halo_enumerator import HaloEnumerator
+from .python_frontend import PythonToStencilModel, get_ast
+from .stencil_exception import StencilException
+
+
+def product(nums):
+    """Product of an iterable of numbers (reference ``stencil_kernel.py:54-58``)."""
+    result = 1
+    for x in nums:
+        result *= x
+    return result
+
+
+StencilArgConfig = namedtuple('StencilArgConfig', ['size', 'dtype', 'ndim', 'shape'])
+
+
+def _backend_table():
+    # imported lazily: building a Stencil must not need the CUDA shim
+    from .backend.cuda.transformer import StencilCudaTransformer
+    return {"cuda": StencilCudaTransformer}
+
+
+class SpecializedStencil(object):
+    """JIT driver for one ``Stencil`` instance and one backend."""
+
+    def __init__(self, stencil_kernel, backend_name, boundary_handling=""):
+        self.kernel = stencil_kernel
+        self.backend_name = backend_name
+        self.backend = _backend_table()[backend_name]
+        self.backend_key = "{}_{}".format(backend_name, boundary_handling)
+        self.original_tree = get_ast(stencil_kernel.kernel)
+        self._cache = {}
+        self.args = None
+
+    @staticmethod
+    def _describe(arg):
+        try:
+            shape = tuple(int(s) for s in arg.shape)
+            if hasattr(arg, 'detach') and hasattr(arg, 'data_ptr'):      # torch tensor
+                import torch
+                dtype = np.dtype(str(arg.dtype).replace('torch.', ''))
+                del torch
+            else:
+                dtype = np.dtype(arg.dtype)
+            return StencilArgConfig(shape[0] if shape else 0, dtype, len(shape), shape)
+        except (AttributeError, TypeError):
+            raise StencilException("stencil arguments must be numpy arrays or torch tensors, "
+                                   "got {}".format(type(arg)))
+
+    def args_to_subconfig(self, args):
+        """Cache key of a call (reference ``:244-256``): (len, dtype, ndim, shape) per argument."""
+        self.args = args
+        return tuple(self._describe(arg) for arg in args)
+
+    def transform(self, arg_cfg):
+        """Python AST -> semantic model -> CUDA plan (reference ``:278-344``)."""
+        model = PythonToStencilModel().visit(self.original_tree)
+        transformer = self.backend(self.args, None, self.kernel, arg_cfg=arg_cfg,
+                                   fusable_nodes=None)
+        return transformer.visit(model)
+
+    def finalize(self, plan):
+        """Plan -> callable (reference ``:346-410``)."""
+        from .backend.cuda.runtime import ConcreteCudaStencil
+        return ConcreteCudaStencil(plan)
+
+    def specialize(self, args):
+        if len(args) == 0:
+            raise StencilException("a stencil needs at least one input grid")
+        arg_cfg = self.args_to_subconfig(args)
+        concrete = self._cache.get(arg_cfg)
+        if concrete is None:
+            concrete = self.finalize(self.transform(arg_cfg))
+            self._cache[arg_cfg] = concrete
+        return concrete
+
+    def __call__(self, *args, **kwargs):
+        return self.specialize(args)(*args, **kwargs)
+
+
+class Stencil(object):
+    """
+    Abstract base of all stencils: subclasses define ``kernel`` and, unless ``neighborhoods`` is
+    passed to ``__init__``, a class-level ``neighborhoods`` list of lists of offset tuples.
+    """
+    backend_dict = {"cuda": "cuda", "python": None,
+                    # names the reference knows; not executable in this build
+                    "c": None, "omp": None, "ocl": None, "opencl": None}
+
+    boundary_handling_list = ['clamp', 'zero', 'copy', 'wrap']
+    composable = True
+
+    def __call__(self, *args, **kwargs):
+        return self.specializer(*args, **kwargs)
+
+    def __init__(self, backend='cuda', neighborhoods=None, boundary_handling='clamp', **kwargs):
+        """
+        :param backend: 'cuda' (sm_100a JIT, default) or 'python' (literal interpreter)
+        :param neighborhoods: list of neighborhoods, each a list of offset tuples; overrides the
+            class attribute of the same name
+        :param boundary_handling: one of 'clamp', 'zero', 'copy', 'wrap'.  As in the reference
+            (``stencil_kernel.py:509``: the flag is spelt ``is_warped == 'warp'`` and never read)
+            'wrap' behaves exactly like 'zero'.
+        :raise StencilException: on missing neighborhoods or unknown boundary handling
+        """
+        if neighborhoods:
+            self.neighborhood_definition = neighborhoods
+        else:
+            try:
+                self.neighborhood_definition = self.neighborhoods
+            except Exception:
+                raise StencilException(
+                    "Error: neighborhoods must be defined by {}".format(type(self)))
+
+        if backend not in self.backend_dict:
+            raise StencilException("Error: unknown backend '{}'".format(backend))
+        if backend not in ('cuda', 'python'):
+            raise StencilException(
+                "Error: backend '{}' is not part of this build; use backend='cuda' (or 'python' "
+                "for the literal interpreter)".format(backend))
+        self.backend = self.backend_dict[backend]
+        self.backend_name = backend
+
+        if boundary_handling not in Stencil.boundary_handling_list:
+            raise StencilException(
+                "Error: boundary handling value '{}' not recognized".format(boundary_handling))
+
+        self.boundary_handling = boundary_handling
+        self.is_clamped = boundary_handling == 'clamp'
+        self.is_warped = boundary_handling == 'warp'      # sic, reference :509
+        self.is_copied = boundary_handling == 'copy'
+        self.is_zeroed = boundary_handling == 'zero'
+
+        # communicates the shape from interior_points to neighbors (clamping); not re-entrant
+        self.current_shape = None
+
+        try:
+            self.dim = len(self.neighborhood_definition[0][0])
+        except Exception:
+            raise StencilException(
+                "Error: neighborhoods not properly set for {}".format(type(self)))
+
+        self.ghost_depth = self.compute_ghost_depth()
+
+        if backend == 'python':
+            self.specializer = self.python_kernel_wrapper
+        else:
+            self.specializer = SpecializedStencil(self, backend, boundary_handling)
+        self.model = self.kernel
+
+        # accepted and, as in the reference (:534-536), not acted upon
+        self.should_unroll = kwargs.get('should_unroll', True)
+        self.should_cacheblock = kwargs.get('should_cacheblock', False)
+        self.block_size = kwargs.get('block_size', 1)
+
+        self.specialized_sizes = None
+
+    @abc.abstractmethod
+    def kernel(self, *args):
+        """subclasses must implement this"""
+        return
+
+    def python_kernel_wrapper(self, *args):
+        """Literal execution: zeroed output, run ``kernel``, then copy the halo if asked
+        (reference ``:545-559``)."""
+        input_grid = args[0]
+        output = np.zeros_like(input_grid)
+        self.kernel(*(args + (output,)))
+
+        if self.is_copied:
+            for point in self.halo_points(input_grid):
+                output[point] = input_grid[point]
+        return output
+
+    @property
+    def constants(self):
+        """name -> value map; names are replaced by literals at specialisation
+        (reference ``:561-563``, ``backend/stencil_backend.py:127-130``)."""
+        return {}
+
+    def compute_ghost_depth(self):
+        """Per-dimension max |offset| over all neighborhoods (reference ``:565-579``)."""
+        depth = [0] * self.dim
+        for neighborhood in self.neighborhood_definition:
+            for neighbor in neighborhood:
+                for d in range(self.dim):
+                    depth[d] = max(depth[d], abs(neighbor[d]))
+        return tuple(depth)
+
+    def interior_points(self, x, stride=1):
+        """Iterate the points the kernel body runs on (reference ``:581-605``): every point when
+        clamping, otherwise the points at least ``ghost_depth`` away from each face.  Records
+        ``x.shape`` for ``neighbors`` when clamping, so it is not re-entrant."""
+        if self.is_clamped:
+            self.current_shape = x.shape
+            ranges = [range(0, extent, stride) for extent in x.shape]
+        else:
+            ranges = [range(self.ghost_depth[d], extent - self.ghost_depth[d], stride)
+                      for d, extent in enumerate(x.shape)]
+        for item in itertools.product(*ranges):
+            yield tuple(item)
+
+    def neighbors(self, point, neighbors_id=0):
+        """Absolute neighbor points of ``point`` (reference ``:607-630``), clamped into the grid
+        last seen by ``interior_points`` when boundary handling is 'clamp'."""
+        try:
+            neighborhood = self.neighborhood_definition[neighbors_id]
+        except IndexError:
+            raise StencilException(
+                "Undefined neighborhood identifier {} this stencil has {}".format(
+                    neighbors_id, len(self.neighborhood_definition)))
+        if self.is_clamped and self.current_shape is not None:
+            shape = self.current_shape
+            for neighbor in neighborhood:
+                yield tuple(Stencil.clamp(point[d] + neighbor[d], 0, shape[d])
+                            for d in range(len(point)))
+        else:
+            for neighbor in neighborhood:
+                yield tuple(p + n for p, n in zip(point, neighbor))
+
+    def interior_points_slice(self, extra=0):
+        """Tuple of slices selecting the interior of a grid (reference ``:632-641``)."""
+        return tuple(slice(g + extra, -(g + extra)) for g in self.ghost_depth)
+
+    def distance(self, x, y):
+        """Euclidean distance; override to attach a weight to each neighbor offset
+        (reference ``:643-650``)."""
+        return math.sqrt(sum((x[i] - y[i]) ** 2 for i in range(len(x))))
+
+    @staticmethod
+    def clamp(x, min_x, max_x):
+        return max(min_x, min(x, max_x - 1))
+
+    def halo_points(self, grid):
+        """Points of ``grid`` within ghost depth of a face (reference ``:656-664``)."""
+        for halo_point in HaloEnumerator(self.ghost_depth, grid.shape):
+            yield halo_point
+
+    # ---- additive API --------------------------------------------------------------------------
+    def iterate(self, grid, iterations, *tables, **kwargs):
+        """``iterations`` applications ``g = stencil(g, *tables)`` with the grid kept on the
+        device between sweeps (the reference has no such call; its users loop in Python)."""
+        if self.backend_name == 'python':
+            for _ in range(iterations):
+                grid = self(grid, *tables)
+            return grid
+        return self.specializer.specialize((grid,) + tables).iterate(
+            grid, iterations, *tables, **kwargs)
