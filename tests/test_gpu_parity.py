@@ -1,0 +1,165 @@
+"""GPU parity: backend='cuda' against the CPU oracle (restated reference C), bit for bit.
+
+Every comparison is on the FULL grid (halo included) and on bit patterns: float32 results are
+compared as uint32.  Float tolerance used anywhere in this file: none -- summation order is
+preserved and FMA contraction is off, so the north-star's "bit-exact" branch applies to every
+case here (the <= 4 ulp branch is not needed).
+"""
+import glob
+import os
+
+import numpy
+import pytest
+
+from cases import CASES, CASE_MODE_PAIRS, PAIR_IDS, oracle_output
+from stencil_code_b200.stencil_exception import StencilException
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STRATEGIES = ("direct", "auto")
+
+
+def bits(array):
+    array = numpy.ascontiguousarray(array)
+    return array.view(numpy.uint32 if array.dtype == numpy.float32 else numpy.uint64)
+
+
+def assert_bit_identical(actual, expected):
+    assert actual.shape == expected.shape and actual.dtype == expected.dtype
+    different = bits(actual) != bits(expected)
+    if different.any():
+        where = numpy.argwhere(different)
+        first = tuple(where[0])
+        raise AssertionError("{} of {} elements differ; first at {}: got {!r}, expected {!r}".format(
+            int(different.sum()), different.size, first, actual[first], expected[first]))
+
+
+def set_strategy(monkeypatch, strategy):
+    if strategy == "auto":
+        monkeypatch.delenv("STENCIL_CUDA_STRATEGY", raising=False)
+    else:
+        monkeypatch.setenv("STENCIL_CUDA_STRATEGY", strategy)
+
+
+@pytest.mark.parametrize("strategy", STRATEGIES)
+@pytest.mark.parametrize("case,mode", CASE_MODE_PAIRS, ids=PAIR_IDS)
+def test_small_grids_match_oracle(case, mode, strategy, monkeypatch):
+    set_strategy(monkeypatch, strategy)
+    grid = case.grid(seed=1)
+    expected = oracle_output(case.make(mode, 'python'), grid, *case.extra)
+    actual = case.make(mode, 'cuda')(grid, *case.extra)
+    assert isinstance(actual, numpy.ndarray)
+    assert_bit_identical(actual, expected)
+
+
+@pytest.mark.parametrize("case,mode", [(c, m) for c, m in CASE_MODE_PAIRS if c.golden],
+                         ids=["{}-{}".format(c.name, m) for c, m in CASE_MODE_PAIRS if c.golden])
+def test_reference_made_fixtures(case, mode):
+    """Integer-valued fixtures computed by the unmodified reference: exact equality (interior only
+    for distance-weighted clamp cases, see tests/test_oracle_golden.py)."""
+    from test_oracle_golden import comparable, INEXACT
+    data = numpy.load(os.path.join(GOLDEN, "{}__{}.npz".format(case.name, mode)))
+    stencil = case.make(mode, 'cuda')
+    actual = comparable(case, mode, stencil, stencil(data["exact_in"], *case.extra))
+    expected = comparable(case, mode, stencil, data["exact_out"])
+    if case.name in INEXACT:
+        scale = float(numpy.abs(expected).max())
+        numpy.testing.assert_array_almost_equal(actual / scale, expected / scale, decimal=6)
+    else:
+        numpy.testing.assert_array_equal(actual, expected)
+
+
+# shapes that exercise tile edges, unaligned rows, thin grids, and TMA-eligible rows
+SHAPE_SWEEP = {
+    "laplacian": [(5, 5, 5), (3, 4, 7), (33, 20, 132), (16, 40, 256), (70, 37, 64), (4, 130, 136)],
+    "jacobi3d": [(40, 24, 128), (19, 65, 260)],
+    "simple_moore": [(5, 5), (102, 7), (64, 128), (130, 260), (37, 1024), (300, 516)],
+    "convolution5_modes": [(8, 8), (64, 128), (131, 388), (50, 1028)],
+    "diagnostic": [(8, 8), (96, 256), (45, 132)],
+    "two_d_heat": [(16, 16, 16), (9, 34, 128)],
+    "laplacian27": [(32, 32, 32), (10, 33, 136)],
+    "cross3d_r2": [(12, 20, 128), (9, 9, 12)],
+    "odd_weights": [(64, 128), (33, 36)],
+    "stencil1d": [(8,), (1000,), (4096,)],
+    "better_bilateral": [(64, 32), (40, 128)],
+}
+SWEEP = [(case, mode, shape) for case in CASES if case.name in SHAPE_SWEEP
+         for mode in case.modes for shape in SHAPE_SWEEP[case.name]]
+
+
+@pytest.mark.parametrize("case,mode,shape", SWEEP,
+                         ids=["{}-{}-{}".format(c.name, m, "x".join(map(str, s))) for c, m, s in SWEEP])
+def test_shape_sweep_matches_oracle(case, mode, shape):
+    grid = case.grid(seed=2, shape=shape)
+    expected = oracle_output(case.make(mode, 'python'), grid, *case.extra)
+    assert_bit_identical(case.make(mode, 'cuda')(grid, *case.extra), expected)
+
+
+def test_float64_grid():                       # reference test_boundary_handling.py:56 uses float64
+    from stencil_code_b200.library.diagnostic_stencil import DiagnosticStencil
+    grid = numpy.random.RandomState(5).random_sample((20, 24)) * 1000
+    for mode in ('clamp', 'zero', 'copy'):
+        expected = oracle_output(DiagnosticStencil(backend='python', boundary_handling=mode), grid)
+        actual = DiagnosticStencil(backend='cuda', boundary_handling=mode)(grid)
+        assert actual.dtype == numpy.float64
+        assert_bit_identical(actual, expected)
+
+
+def test_strict_double_mode_equals_demoted_mode(monkeypatch):
+    """The exact float32 demotion must not change a bit (normal-range inputs)."""
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    from stencil_code_b200.library.two_d_heat import TwoDHeatFlow
+    for make, shape in ((lambda: Jacobi3D(1.0, 0.25), (12, 16, 128)),
+                        (lambda: TwoDHeatFlow(), (8, 16, 128))):
+        grid = (numpy.random.RandomState(7).random_sample(shape) * 1000).astype(numpy.float32)
+        monkeypatch.delenv("STENCIL_CUDA_STRICT", raising=False)
+        demoted = make()(grid)
+        monkeypatch.setenv("STENCIL_CUDA_STRICT", "1")
+        strict = make()(grid)
+        assert_bit_identical(demoted, strict)
+        assert_bit_identical(demoted, oracle_output(make(), grid))
+
+
+def test_torch_tensor_in_torch_tensor_out():
+    import torch
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    grid = (numpy.random.RandomState(9).random_sample((16, 24, 128)) * 1000).astype(numpy.float32)
+    expected = oracle_output(LaplacianKernel(backend='python'), grid)
+    result = LaplacianKernel()(torch.from_numpy(grid).cuda())
+    assert isinstance(result, torch.Tensor) and result.is_cuda
+    assert_bit_identical(result.cpu().numpy(), expected)
+
+
+def test_iterate_equals_repeated_calls():
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    grid = numpy.random.RandomState(11).random_sample((24, 16, 128)).astype(numpy.float32)
+    stencil = Jacobi3D(1.0, 0.25)
+    looped = grid
+    for _ in range(5):
+        looped = stencil(looped)
+    assert_bit_identical(stencil.iterate(grid, 5), looped)
+    reference = grid
+    python_side = Jacobi3D(1.0, 0.25, backend='python')
+    for _ in range(5):
+        reference = oracle_output(python_side, reference)
+    assert_bit_identical(looped, reference)
+
+
+def test_wrong_shape_raises_type_error():
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    stencil = LaplacianKernel()
+    stencil(numpy.zeros((8, 8, 8), numpy.float32))
+    concrete = stencil.specializer.specialize((numpy.zeros((8, 8, 8), numpy.float32),))
+    with pytest.raises(TypeError):
+        concrete(numpy.zeros((8, 8, 9), numpy.float32))
+
+
+def test_product_never_imports_the_oracle():
+    import sys
+    import subprocess
+    code = ("import sys, numpy; sys.path.insert(0, '.');"
+            "from stencil_code_b200.library.laplacian import LaplacianKernel;"
+            "LaplacianKernel()(numpy.ones((8, 8, 8), numpy.float32));"
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", code], cwd=root, check=True)

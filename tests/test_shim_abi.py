@@ -1,0 +1,40 @@
+"""The C-ABI library loads on a GPU-less host and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+from stencil_code_b200.backend.cuda import runtime
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "stencil_cuda.h")) as handle:
+        text = handle.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 40
+    raw = ctypes.CDLL(runtime.LIBRARY_PATH)
+    for name in names:
+        assert hasattr(raw, name), name
+    assert set(names) == set(runtime.SYMBOLS), set(names) ^ set(runtime.SYMBOLS)
+
+
+def test_abi_version_and_error_string():
+    library = runtime.load_library()
+    assert library.sc_abi_version() == 1
+    module = ctypes.c_void_p()
+    code = library.sc_compile(b"this is not CUDA", b"bad.cu", None, 0, ctypes.byref(module))
+    assert code == -3                                   # SC_ECOMPILE
+    assert b"bad.cu" in library.sc_last_error()
+
+
+def test_nvrtc_compiles_sm100a_cubin_without_a_gpu():
+    module = runtime.compile_source('extern "C" __global__ void k(float* p) { p[threadIdx.x] = 1.0f; }',
+                                    "tiny.cu", ("--fmad=false",))
+    cubin = module.cubin()
+    assert cubin[:4] == b"\x7fELF" and len(cubin) > 1000
