@@ -1,5 +1,739 @@
-"""Strategy 'stream' (placeholder until the TMA streaming generator lands)."""
+"""Strategy 'stream': TMA-staged shared-memory tiles streamed along axis 0.
+
+The fast path for float32 grids of rank 2 and 3.  It supersedes the reference's OpenCL kernel
+(``backend/ocl.py:363-594``: one work-item per point, a ``__local`` tile of the first argument
+filled by a strided cooperative load with a div/mod and a per-dimension clamp per element, a
+barrier, taps from local memory) and its per-dimension halo-copy kernels
+(``backend/ocl_boundary_copier.py:97-134``).  The design, B200-first:
+
+  * A CTA owns a tile of the fast axes (3-d: TY rows x TX columns of a plane; 2-d: TX columns)
+    and marches along axis 0 over a chunk of planes (3-d) / rows (2-d).
+  * One producer warp feeds a ring of S shared-memory stages with ``cp.async.bulk.tensor``
+    (TMA) boxes that include the halo; completion is tracked by mbarriers, consumer warps hand
+    stages back through a second set of mbarriers.  TMA zero-fills what lies outside the grid.
+  * Each consumer thread computes a register block of BY rows x 4 consecutive columns per plane.
+    Values needed from several planes of the sweep are loaded from shared memory ONCE, when the
+    plane is newest, and kept in a rotating register window (the loop is emitted once per window
+    phase so that rotation is pure renaming).  Stencils whose window would not fit in registers
+    (bilateral filter, radius 9) read every tap row from the shared-memory ring instead.
+  * All four boundary modes live in the same kernel.  Along axis 0 the producer clamps the TMA
+    coordinate; inside the plane the producer warp overwrites the zero-filled out-of-grid halo
+    cells of boundary tiles with the clamped values before releasing the stage ('clamp');
+    'zero'/'copy' select 0 / the centre value for halo points at the store.  Every output point
+    of the launch is written exactly once, with 128-bit stores.
+  * Arithmetic is the typed per-point program, statement for statement, with FMA contraction
+    off -- bit-identical to the direct strategy and to the reference's C.
+
+Algorithmic traffic: 8 B per point (one float32 read, one write).  Roofline: HBM bandwidth.
+"""
+from ...stencil_exception import StencilException
+from .. import point_program as pp
+import re
+
+from .codegen_common import PROLOGUE, emit_statements
+
+_LOCAL_NAME = re.compile(r'\b_t_[A-Za-z0-9_]+\b')
+
+FUNCTION = "stencil_stream"
+
+PTX_HELPERS = r'''
+struct alignas(64) TensorMap { u64 opaque[16]; };
+
+__device__ __forceinline__ u32 sc_smem(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(sc_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sc_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(sc_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(sc_smem(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const TensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(tm) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const TensorMap* tm, u64* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(sc_smem(dst)), "l"(tm), "r"(sc_smem(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* tm, u64* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(sc_smem(dst)), "l"(tm), "r"(sc_smem(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+'''
+
+
+class TensorMapSpec(object):
+    """What the runtime needs to encode one TMA descriptor (``sc_tensormap_tiled``)."""
+    def __init__(self, arg, dims, strides_bytes, box, dtype_code=0, tag=""):
+        self.arg = arg
+        self.dims = tuple(int(d) for d in dims)
+        self.strides_bytes = tuple(int(s) for s in strides_bytes)
+        self.box = tuple(int(b) for b in box)
+        self.dtype_code = dtype_code
+        self.key = (arg, self.dims, self.strides_bytes, self.box, dtype_code, tag)
+
+
+class StreamConfig(object):
+    """Tile / pipeline shape of one generated streaming kernel."""
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def describe(self):
+        keys = ("rank", "TX", "TY", "BY", "U", "S", "NCW", "PADX", "HY", "HZ_LO", "HZ_HI", "W",
+                "mode", "blocks_per_sm", "smem_bytes")
+        return {k: getattr(self, k) for k in keys}
+
+
+# ---- applicability ------------------------------------------------------------------------------
+def _grid_args(program):
+    return [a for a in program.args if a.used_as_grid]
 
 
 def applicable(program, domain, device_props):
-    return False, "stream strategy not built yet"
+    if program.dim not in (2, 3):
+        return False, "rank {} (stream handles 2 and 3)".format(program.dim)
+    if program.out_ctype != pp.FLOAT:
+        return False, "output is not float32"
+    for arg in _grid_args(program):
+        if arg.ctype != pp.FLOAT:
+            return False, "grid argument '{}' is not float32".format(arg.name)
+    n_fast = program.shape[-1]
+    if n_fast % 4 != 0:
+        return False, "rows of {} floats are not a multiple of 16 bytes (TMA stride rule)".format(n_fast)
+    if n_fast < 32:
+        return False, "rows shorter than 32 floats"
+    if program.dim == 3 and program.shape[1] < 4:
+        return False, "fewer than 4 rows per plane"
+    if program.shape[0] < 2:
+        return False, "a single plane/row along the streaming axis"
+    if program.npoints < 4096:
+        return False, "tiny grid"
+    lo, hi = program.tap_extent()
+    if max(-lo[-1], hi[-1]) > 12:
+        return False, "tap radius along the fast axis above 12"
+    if any(s >= 2 ** 31 for s in program.shape):
+        return False, "dimension above 2^31"
+    try:
+        choose_config(program, domain, device_props)
+    except StencilException as error:
+        return False, str(error)
+    return True, "float32 rank-{} grid with 16-byte rows".format(program.dim)
+
+
+# ---- footprint analysis -------------------------------------------------------------------------
+def _tap3(offset):
+    """(d_stream, d_row, d_col) of a tap offset for rank 2 or 3."""
+    if len(offset) == 3:
+        return offset
+    return (offset[0], 0, offset[1])
+
+
+class Footprint(object):
+    """Which shared-memory values one thread needs, and at which ages of the streamed plane.
+
+    ``age`` is the axis-0 offset of a plane relative to the output plane (the tap's first
+    component).  A value is identified by (grid, row, col) relative to the thread's register
+    block; ``ages[(g, row, col)]`` is the set of ages at which it is used.
+    """
+    def __init__(self, program, BY, copy_center):
+        self.ages = {}
+        for tap in program.taps():
+            dz, dy, dx = _tap3(tap.offset)
+            for b in range(BY):
+                for j in range(4):
+                    self.ages.setdefault((tap.arg, b + dy, j + dx), set()).add(dz)
+        if copy_center:
+            for b in range(BY):
+                for j in range(4):
+                    self.ages.setdefault((0, b, j), set()).add(0)
+        all_ages = [a for s in self.ages.values() for a in s] or [0]
+        self.hz_lo, self.hz_hi = min(min(all_ages), 0), max(max(all_ages), 0)
+        self.window = self.hz_hi - self.hz_lo + 1
+        self.window_registers = sum(max(s) - min(s) + 1 for s in self.ages.values())
+        # age at which the last first-load of a plane happens: the plane may leave smem after it
+        self.release_age_regwin = min(max(s) for s in self.ages.values())
+
+
+def choose_config(program, domain, device_props, override=None):
+    """Pick tile shape, register block, ring depth and occupancy for a stencil and device."""
+    rank = program.dim
+    lo, hi = program.tap_extent()
+    hx = max(-lo[-1], hi[-1])
+    hy = max(-lo[1], hi[1]) if rank == 3 else 0
+    PADX = 4 * ((hx + 3) // 4) if hx else 0
+    copy_center = program.boundary == 'copy'
+    n_fast = program.shape[-1]
+    n_grids = len(_grid_args(program))
+    override = override or {}
+
+    candidates = []
+    if rank == 3:
+        for TY, BY, NCW in ((32, 4, 8), (16, 4, 4), (32, 2, 16), (16, 2, 8), (8, 2, 4), (8, 1, 8)):
+            candidates.append(dict(TX=128, TY=TY, BY=BY, NCW=NCW, U=1))
+    else:
+        # rank 2: every consumer warp owns a 128-column sub-tile with its own TMA box and halo
+        for NCW, U in ((4, 8), (8, 8), (4, 16), (2, 16), (2, 8), (1, 16), (1, 8)):
+            candidates.append(dict(TX=NCW * 128, TY=1, BY=1, NCW=NCW, U=U))
+    best = None
+    for cand in candidates:
+        cand.update({k: v for k, v in override.items() if k in cand})
+        fp = Footprint(program, cand['BY'], copy_center)
+        mode = override.get('mode') or ('regwin' if fp.window_registers <= 160 else 'smem')
+        W = fp.window
+        if mode == 'regwin':
+            resident_units = fp.hz_hi - fp.release_age_regwin + 1
+        else:
+            resident_units = W
+        U = cand['U']
+        if rank == 2 and U <= max(-fp.hz_lo, fp.hz_hi):
+            continue
+        resident_stages = (resident_units + U - 1) // U + (1 if U > 1 else 0)
+        prefetch = override.get('prefetch', 3 if rank == 3 else 2)
+        S = resident_stages + prefetch
+        pitch = 128 + 2 * PADX
+        if pitch > 256:
+            continue
+        rows = (cand['TY'] + 2 * hy) if rank == 3 else U
+        n_sub = 1 if rank == 3 else cand['NCW']
+        stage_floats = n_sub * rows * pitch
+        stage_bytes = stage_floats * 4
+        stage_bytes_aligned = (stage_bytes + 127) // 128 * 128
+        smem = n_grids * S * stage_bytes_aligned + 3 * S * 8 + 128
+        threads = (cand['NCW'] + 1) * 32
+        if smem > device_props.smem_per_block_optin:
+            continue
+        blocks_per_sm = min(device_props.smem_per_sm // (smem + 1024),
+                            device_props.max_threads_per_sm // threads, 8)
+        if blocks_per_sm < 1:
+            continue
+        # wider tiles than the grid waste lanes; prefer the tile that wastes least, then the one
+        # with the smallest halo overhead, then more resident warps
+        waste_x = (-(-n_fast // cand['TX']) * cand['TX']) / float(n_fast)
+        waste_y = 1.0
+        halo = 1.0
+        if rank == 3:
+            n_rows = program.shape[1]
+            waste_y = (-(-n_rows // cand['TY']) * cand['TY']) / float(n_rows)
+            halo = (cand['TY'] + 2 * hy) * pitch / float(cand['TY'] * cand['TX'])
+        else:
+            halo = pitch / 128.0
+        resident_warps = blocks_per_sm * cand['NCW']
+        score = (waste_x * waste_y * halo) * (1.0 if resident_warps >= 12 else 1.15)
+        config = StreamConfig(rank=rank, PADX=PADX, HX=hx, HY=hy, HZ_LO=fp.hz_lo, HZ_HI=fp.hz_hi, W=W,
+                              mode=mode, S=S, PITCH=pitch, ROWS=rows, STAGE_FLOATS=stage_bytes_aligned // 4,
+                              STAGE_BYTES=stage_bytes, smem_bytes=smem, threads=threads, NSUB=n_sub,
+                              SUB_FLOATS=rows * pitch,
+                              blocks_per_sm=blocks_per_sm, footprint=fp, n_grids=n_grids,
+                              score=score, **cand)
+        if best is None or score < best.score - 1e-9:
+            best = config
+    if best is None:
+        raise StencilException("no streaming tile fits this stencil in shared memory")
+    return best
+
+
+def plan_chunks(n_units, tiles, slots, window, min_chunk):
+    """Number of axis-0 chunks so that tiles*chunks fills the resident CTA slots in whole waves
+    while the window start-up (window-1 extra units per chunk) stays small."""
+    best_chunks, best_score = 1, -1.0
+    max_chunks = max(1, n_units // max(min_chunk, 1))
+    for chunks in range(1, max_chunks + 1):
+        length = -(-n_units // chunks)
+        if chunks > 1 and length < min_chunk:
+            break
+        items = tiles * (-(-n_units // length))
+        waves = -(-items // slots)
+        fill = items / float(waves * slots)
+        overhead = length / float(length + window - 1)
+        score = fill * overhead
+        if score > best_score + 1e-9:
+            best_chunks, best_score = chunks, score
+    return best_chunks
+
+
+# ---- code generation ----------------------------------------------------------------------------
+class _Emitter(object):
+    def __init__(self):
+        self.lines = []
+        self.level = 0
+
+    def __call__(self, text=""):
+        self.lines.append(("    " * self.level + text) if text else "")
+
+    def open(self, text):
+        self(text + " {")
+        self.level += 1
+
+    def close(self, suffix=""):
+        self.level -= 1
+        self("}" + suffix)
+
+    def text(self):
+        return "\n".join(self.lines) + "\n"
+
+
+def _group_loads(cols):
+    """Split a set of needed columns (relative to the thread's first column) into aligned
+    128-bit / 64-bit / 32-bit shared-memory loads.  Returns [(first_col, width, used_cols)]."""
+    loads = []
+    quads = sorted({c // 4 for c in cols})
+    for q in quads:
+        used = sorted(c for c in cols if c // 4 == q)
+        if len(used) >= 3:
+            loads.append((4 * q, 4, used))
+        elif len(used) == 2 and used[0] % 2 == 0 and used[1] == used[0] + 1:
+            loads.append((used[0], 2, used))
+        else:
+            for c in used:
+                loads.append((c, 1, [c]))
+    return loads
+
+
+def generate(program, domain, cfg):
+    rank = cfg.rank
+    fp = cfg.footprint
+    grids = _grid_args(program)
+    ring_of = {arg.index: k for k, arg in enumerate(grids)}        # ring index per grid argument
+    shape = program.shape
+    N0 = shape[0]
+    N1 = shape[1] if rank == 3 else 1
+    N2 = shape[-1]
+    TX, TY, BY, U, S, NCW = cfg.TX, cfg.TY, cfg.BY, cfg.U, cfg.S, cfg.NCW
+    PADX, HX, HY, PITCH, ROWS = cfg.PADX, cfg.HX, cfg.HY, cfg.PITCH, cfg.ROWS
+    HZ_LO, HZ_HI, W = cfg.HZ_LO, cfg.HZ_HI, cfg.W
+    SF = cfg.STAGE_FLOATS
+    NSUB, SUBF = cfg.NSUB, cfg.SUB_FLOATS
+    regwin = cfg.mode == 'regwin'
+    phases = W if regwin else 1
+    boundary = program.boundary
+    clamp = boundary == 'clamp'
+    copy = boundary == 'copy'
+    c_lo, c_hi = domain.clamp_lo, domain.clamp_hi
+    i_lo, i_hi = domain.interior_lo, domain.interior_hi
+    col_axis = rank - 1
+    needs_patch = clamp and (HX > 0 or HY > 0)
+    release_age = fp.release_age_regwin if regwin else HZ_LO
+    rel_back = HZ_HI - release_age
+
+    # tables: constant-index entries are hoisted into registers, data-indexed small tables go to smem
+    data_tables, const_refs = set(), {}
+    for node in program.walk():
+        if isinstance(node, pp.TableRef):
+            constant = _const_index(node.index)
+            if constant is None:
+                data_tables.add(node.arg)
+            else:
+                const_refs[(node.arg, constant)] = node.ctype
+    smem_tables = {a.index: a for a in program.args if not a.used_as_grid
+                   and a.index in data_tables and a.size * a.dtype.itemsize <= 8192}
+    guard_halo_body = (not clamp) and bool(data_tables)
+
+    def tag(v):
+        return "m{}".format(-v) if isinstance(v, int) and v < 0 else str(v)
+
+    def value_name(g, where, row, col):
+        return "v{}_{}_{}_{}".format(g, tag(where), tag(row), tag(col))
+
+    def slot_of(phase, age, key):
+        ages = fp.ages[key]
+        if max(ages) == min(ages):
+            return 0
+        return (phase + age - HZ_HI) % W
+
+    def name_of(phase, g, age, row, col):
+        if regwin:
+            return value_name(g, slot_of(phase, age, (g, row, col)), row, col)
+        return value_name(g, "a" + tag(age), row, col)
+
+    e = _Emitter()
+    e.lines.append(PROLOGUE)
+    e.lines.append(PTX_HELPERS)
+    e("// stream strategy: rank {} grid {} boundary {} | tile TX={} TY={} BY={} U={} ring S={} "
+      "window W={} ({})".format(rank, shape, boundary, TX, TY, BY, U, S, W, cfg.mode))
+    params = ["const {}* __restrict__ a{}".format(arg.ctype, arg.index) for arg in program.args]
+    for arg in grids:
+        params.append("const __grid_constant__ TensorMap tm{}".format(arg.index))
+    params += ["float* __restrict__ out", "int a0_begin", "int a0_end", "int chunk_len"]
+    e('extern "C" __global__ void __launch_bounds__({}, {})'.format(cfg.threads, cfg.blocks_per_sm))
+    e("{}({})".format(FUNCTION, ", ".join(params)))
+    e.open("")
+    e("extern __shared__ __align__(128) unsigned char smem_raw[];")
+    e("float* const ring = reinterpret_cast<float*>(smem_raw);")
+    e("u64* const bar_full = reinterpret_cast<u64*>(smem_raw + {});".format(cfg.n_grids * S * SF * 4))
+    e("u64* const bar_empty = bar_full + {};".format(S))
+    e("u64* const bar_land = bar_empty + {};".format(S))
+    for index, arg in sorted(smem_tables.items()):
+        e("__shared__ {} tab{}[{}];".format(arg.ctype, index, arg.size))
+    e("const int tid = threadIdx.x;")
+    e("const int warp = tid >> 5;")
+    e("const int lane = tid & 31;")
+    e("const int x0 = blockIdx.x * {};".format(TX))
+    if rank == 3:
+        e("const int y0 = blockIdx.y * {};".format(TY))
+    e("const int u_begin = a0_begin + blockIdx.z * chunk_len;")
+    e("const int u_end = min(u_begin + chunk_len, a0_end);")
+    e("if (u_begin >= u_end) return;")
+    e("const int p_first = u_begin + ({});          // axis-0 index of streamed unit 0".format(HZ_LO))
+    e("const int n_units = (u_end - u_begin) + {};".format(W - 1))
+    e("const int n_stages = (n_units + {}) / {};".format(U - 1, U))
+    e.open("if (tid == 0)")
+    e.open("for (int s = 0; s < {}; ++s)".format(S))
+    e("mbar_init(&bar_full[s], 1);")
+    e("mbar_init(&bar_empty[s], {});".format(NCW))
+    e("mbar_init(&bar_land[s], 1);")
+    e.close()
+    e("fence_barrier_init();")
+    e.close()
+    for index, arg in sorted(smem_tables.items()):
+        e("for (int k = tid; k < {n}; k += {t}) tab{i}[k] = a{i}[k];".format(n=arg.size, t=cfg.threads, i=index))
+    e("__syncthreads();")
+    e()
+
+    # ================================================================== producer warp
+    e.open("if (warp == {})".format(NCW))
+    for arg in grids:
+        e("if (lane == 0) tma_prefetch_desc(&tm{});".format(arg.index))
+    if needs_patch:
+        edges = []
+        if HX:
+            edges += ["x0 == 0", "x0 + {} > {}".format(TX + HX, N2)]
+        if rank == 3 and HY:
+            edges += ["y0 == 0", "y0 + {} > {}".format(TY + HY, N1)]
+        e("const bool patch = {};   // tile touches a clamped face".format(" || ".join(edges)))
+        lag = max(1, S - ((rel_back // U) + 1 + (1 if U > 1 else 0)))
+        e("const int lag = patch ? {} : 0;".format(lag))
+    else:
+        e("const bool patch = false;")
+        e("const int lag = 0;")
+    e.open("for (int k = 0; k < n_stages + lag; ++k)")
+    e.open("if (k < n_stages)")
+    e("const int s = k % {};".format(S))
+    e("if (k >= {S}) mbar_wait(&bar_empty[s], ((k / {S}) - 1) & 1);".format(S=S))
+    e.open("if (lane == 0)")
+    e("u64* const bar = patch ? &bar_land[s] : &bar_full[s];")
+    e("mbar_expect_tx(bar, {});".format(cfg.STAGE_BYTES * cfg.n_grids))
+    if rank == 2:
+        e("const int r0 = p_first + k * {};   // rows outside the grid are zero-filled and never read".format(U))
+    for arg in grids:
+        dst = "ring + ({} + s) * {}".format(ring_of[arg.index] * S, SF)
+        if rank == 3:
+            e("tma_load_3d({dst}, &tm{g}, bar, x0 - {px}, y0 - {hy}, SC_CLAMP(p_first + k, {lo}, {hi}));".format(
+                dst=dst, g=arg.index, px=PADX, hy=HY, lo=c_lo[0], hi=c_hi[0]))
+        else:
+            e.open("for (int w = 0; w < {}; ++w)".format(NSUB))
+            e("float* const dst = {} + w * {};".format(dst, SUBF))
+            e("const int xs = x0 + w * 128 - {};".format(PADX))
+            e("tma_load_2d(dst, &tm{g}, bar, xs, r0);".format(g=arg.index))
+            e.close()
+    e.close()
+    e.close()
+    if needs_patch:
+        e.open("if (patch && k >= lag)")
+        e("const int j = k - lag;")
+        e("const int s = j % {};".format(S))
+        e("mbar_wait(&bar_land[s], (j / {}) & 1);".format(S))
+        for arg in grids:
+            e("float* const st{g} = ring + ({k} + s) * {sf};".format(g=arg.index, k=ring_of[arg.index] * S, sf=SF))
+        # columns first, then whole rows (3-d): corner cells end up clamped in both directions
+        if HX:
+            e.open("for (int w = 0; w < {}; ++w)".format(NSUB))
+            e("const int xs = x0 + w * 128;          // first grid column of this sub-tile")
+            e("if (xs >= {}) break;".format(N2))
+            e("const int col_first = {};".format(PADX))
+            e("const int col_last = {} + min({}, {} - 1 - xs);".format(PADX, 128 + HX - 1, N2))
+            e.open("for (int r = lane; r < {}; r += 32)".format(ROWS))
+            for arg in grids:
+                base = "st{}[w * {} + r * {} + ".format(arg.index, SUBF, PITCH)
+                e.open("if (xs == 0)")
+                e("const float edge = {}col_first];".format(base))
+                for c in range(1, HX + 1):
+                    e("{}col_first - {}] = edge;".format(base, c))
+                e.close()
+                e.open("if (xs + {} > {})".format(128 + HX, N2))
+                e("const float edge = {}col_last];".format(base))
+                for c in range(1, HX + 1):
+                    e("if (col_last + {c} < {p}) {b}col_last + {c}] = edge;".format(c=c, p=PITCH, b=base))
+                e.close()
+            e.close()
+            e.close()
+            e("__syncwarp();")
+        if rank == 3 and HY:
+            e("const int row_last = {} + min({}, {} - 1 - y0);".format(HY, TY + HY - 1, N1))
+            e.open("for (int c = lane; c < {}; c += 32)".format(PITCH))
+            for arg in grids:
+                e.open("if (y0 == 0)")
+                e("const float edge = st{}[{} + c];".format(arg.index, HY * PITCH))
+                for r in range(1, HY + 1):
+                    e("st{}[{} + c] = edge;".format(arg.index, (HY - r) * PITCH))
+                e.close()
+                e.open("if (y0 + {} > {})".format(TY + HY, N1))
+                e("const float edge = st{}[row_last * {} + c];".format(arg.index, PITCH))
+                for r in range(1, HY + 1):
+                    e("if (row_last + {r} < {rows}) st{g}[(row_last + {r}) * {p} + c] = edge;".format(
+                        r=r, rows=ROWS, g=arg.index, p=PITCH))
+                e.close()
+            e.close()
+        e("fence_proxy_async();")
+        e("__syncwarp();")
+        e("if (lane == 0) mbar_arrive(&bar_full[s]);")
+        e.close()
+    e.close()   # for k
+    e("return;")
+    e.close()   # producer
+    e()
+
+    # ================================================================== consumer warps
+    if rank == 3:
+        e("const int tq = lane;                 // quad (4 columns) within the tile row")
+        e("const int tr = warp;                 // group of {} rows".format(BY))
+        e("const int gy = y0 + tr * {};".format(BY))
+        e("const int sbase = ({} + tr * {}) * {} + {} + tq * 4;".format(HY, BY, PITCH, PADX))
+    else:
+        e("const int tq = tid;                  // quad (4 columns) within the CTA's tile")
+        e("const int sbase = warp * {} + {} + lane * 4;   // own 128-column sub-tile".format(SUBF, PADX))
+    e("const int gx = x0 + tq * 4;          // first of this thread's 4 columns")
+    e("const bool col_ok = gx < {};".format(N2))
+    if not clamp:
+        e("u32 halo_mask = 0;                   // bit (b*4+j): the point lies in the in-plane halo")
+        for b in range(BY):
+            for j in range(4):
+                tests = []
+                if rank == 3:
+                    if i_lo[1] > 0:
+                        tests.append("gy + {} < {}".format(b, i_lo[1]))
+                    if i_hi[1] < N1:
+                        tests.append("gy + {} >= {}".format(b, i_hi[1]))
+                if i_lo[col_axis] > 0:
+                    tests.append("gx + {} < {}".format(j, i_lo[col_axis]))
+                if i_hi[col_axis] < N2:
+                    tests.append("gx + {} >= {}".format(j, i_hi[col_axis]))
+                if tests:
+                    e("if ({}) halo_mask |= {}u;".format(" || ".join(tests), 1 << (b * 4 + j)))
+    for (arg, index), ctype in sorted(const_refs.items()):
+        e("const {} tc{}_{} = a{}[{}];".format(ctype, arg, index, arg, index))
+
+    if regwin:
+        names = []
+        for (g, row, col), ages in sorted(fp.ages.items()):
+            slots = W if max(ages) > min(ages) else 1
+            names += [value_name(g, slot, row, col) for slot in range(slots)]
+        for first in range(0, len(names), 8):
+            e("float {};".format(", ".join(n + " = 0.0f" for n in names[first:first + 8])))
+
+    counter = [0]
+
+    def emit_loads(phase, g, age, keys):
+        """shared memory -> registers for the (row, col) values `keys` of grid g at `age`"""
+        pointer = "u{}_{}".format(g, tag(age))
+        decl = "" if regwin else "const float "
+        by_row = {}
+        for (_, row, col) in keys:
+            by_row.setdefault(row, set()).add(col)
+        for row in sorted(by_row):
+            for first, width, used in _group_loads(by_row[row]):
+                offset = row * PITCH + first
+                if width == 1:
+                    e("{}{} = {}[{}];".format(decl, name_of(phase, g, age, row, used[0]), pointer, offset))
+                    continue
+                counter[0] += 1
+                tmp = "q{}".format(counter[0])
+                vec = "float4" if width == 4 else "float2"
+                e("const {v} {t} = *reinterpret_cast<const {v}*>({p} + ({o}));".format(v=vec, t=tmp, p=pointer, o=offset))
+                e(" ".join("{}{} = {}.{};".format(decl, name_of(phase, g, age, row, c), tmp, "xyzw"[c - first])
+                           for c in used))
+
+    def emit_release():
+        e("__syncwarp();")
+        if U == 1:
+            e("if (lane == 0 && unit >= {b}) mbar_arrive(&bar_empty[(unit - {b}) % {S}]);".format(b=rel_back, S=S))
+        else:
+            e.open("if (lane == 0 && unit >= {})".format(rel_back))
+            e("const int ur = unit - {};".format(rel_back))
+            e("if (ur % {u} == {last} && ur / {u} != unit_hi / {u}) mbar_arrive(&bar_empty[(ur / {u}) % {S}]);".format(
+                u=U, last=U - 1, S=S))
+            e.close()
+
+    def table_text(ref, index_text):
+        constant = _const_index(ref.index)
+        if constant is not None:
+            return "tc{}_{}".format(ref.arg, constant)
+        if ref.arg in smem_tables:
+            return "tab{}[{}]".format(ref.arg, index_text)
+        return "a{}[{}]".format(ref.arg, index_text)
+
+    if U > 1:
+        e("// axis-0 clamping is done here: a unit outside [unit_lo, unit_hi] reads the clamped row")
+        e("const int unit_lo = max({} - p_first, 0);".format(c_lo[0]))
+        e("const int unit_hi = {} - p_first;".format(c_hi[0]))
+    e("int unit = 0;                        // newest streamed unit, relative to p_first")
+    e.open("while (true)")
+    for phase in range(phases):
+        e("// ---- window phase {}".format(phase))
+        e("if (unit >= n_units) break;")
+        e.open("")
+        if U == 1:
+            e("mbar_wait(&bar_full[unit % {S}], (unit / {S}) & 1);".format(S=S))
+        else:
+            e("if (unit % {u} == 0) mbar_wait(&bar_full[(unit / {u}) % {S}], (unit / {us}) & 1);".format(
+                u=U, S=S, us=U * S))
+        # where each (grid, age) lives in the ring right now
+        reads = {}
+        for key, ages in fp.ages.items():
+            for age in ([max(ages)] if regwin else sorted(ages)):
+                reads.setdefault((key[0], age), []).append(key)
+        for (g, age) in sorted(reads):
+            back = HZ_HI - age
+            name = "u{}_{}".format(g, tag(age))
+            ring_base = "ring + {}".format(ring_of[g] * S * SF)
+            if U == 1:
+                e("const float* const {n} = {rb} + ((unit + {k} - {b}) % {S}) * {sf} + sbase;".format(
+                    n=name, rb=ring_base, k=S * W, b=back, S=S, sf=SF))
+            else:
+                e("const int i{n} = min(max(unit - {b}, unit_lo), unit_hi);".format(n=name, b=back))
+                e("const float* const {n} = {rb} + ((i{n} / {u}) % {S}) * {sf} + (i{n} % {u}) * {p} + sbase;".format(
+                    n=name, rb=ring_base, u=U, S=S, sf=SF, p=PITCH))
+        if regwin:
+            for (g, age) in sorted(reads):
+                emit_loads(phase, g, age, reads[(g, age)])
+            emit_release()
+
+        # ---- compute output unit z once the window is full
+        e.open("if (unit >= {})".format(W - 1))
+        e("const int z = p_first + unit - ({});".format(HZ_HI))
+        acc = [["acc{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
+        for b in range(BY):
+            e("float {};".format(", ".join(n + " = 0.0f" for n in acc[b])))
+        loaded = set()
+        if not regwin and copy:
+            keys = [(0, b, j) for b in range(BY) for j in range(4)]
+            emit_loads(phase, 0, 0, keys)
+            loaded.update((0, 0, b, j) for b in range(BY) for j in range(4))
+        if not clamp:
+            ztests = []
+            if i_lo[0] > 0:
+                ztests.append("z < {}".format(i_lo[0]))
+            if i_hi[0] < N0:
+                ztests.append("z >= {}".format(i_hi[0]))
+            e("const bool z_halo = {};".format(" || ".join(ztests) if ztests else "false"))
+            e.open("if (!z_halo)")
+        for statement in program.statements:
+            if not regwin:
+                wanted = {}
+                stack = [statement.expr]
+                while stack:
+                    node = stack.pop()
+                    if isinstance(node, pp.Tap):
+                        dz, dy, dx = _tap3(node.offset)
+                        rows = {b + dy for b in range(BY)}
+                        wanted.setdefault((node.arg, dz), set()).update(rows)
+                    stack.extend(node.children())
+                for (g, age), rows in sorted(wanted.items()):
+                    keys = [k for k, ages in fp.ages.items()
+                            if k[0] == g and age in ages and k[1] in rows and (g, age, k[1], k[2]) not in loaded]
+                    if keys:
+                        emit_loads(phase, g, age, keys)
+                        loaded.update((g, age, k[1], k[2]) for k in keys)
+            for b in range(BY):
+                for j in range(4):
+                    def tap_text(tap, b=b, j=j):
+                        dz, dy, dx = _tap3(tap.offset)
+                        return name_of(phase, tap.arg, dz, b + dy, j + dx)
+                    single = pp.PointProgram(program.dim, program.shape, program.out_ctype, program.args,
+                                             [statement], program.ghost_depth, program.boundary)
+                    text = emit_statements(single, tap_text, table_text, acc=acc[b][j], indent="")[0]
+                    text = _LOCAL_NAME.sub(lambda m: "{}_{}_{}".format(m.group(0), b, j), text)
+                    if guard_halo_body:
+                        if isinstance(statement, pp.LocalAssign) and statement.declares:
+                            raise StencilException("local temporaries cannot be combined with data-indexed "
+                                                   "tables under 'zero'/'copy' boundary handling")
+                        text = "if (!(halo_mask & {}u)) {{ {} }}".format(1 << (b * 4 + j), text)
+                    e(text)
+        if not clamp:
+            e.close()   # if (!z_halo)
+            for b in range(BY):
+                for j in range(4):
+                    value = name_of(phase, 0, 0, b, j) if copy else "0.0f"
+                    e("if (z_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), acc[b][j], value))
+        for b in range(BY):
+            if rank == 3:
+                cond = "col_ok && gy + {} < {}".format(b, N1)
+                address = "out + ((i64)z * {} + (gy + {})) * {} + gx".format(N1, b, N2)
+            else:
+                cond = "col_ok"
+                address = "out + (i64)z * {} + gx".format(N2)
+            e("if ({}) st_global_v4({}, {});".format(cond, address, ", ".join(acc[b])))
+        e.close()   # if unit >= W-1
+        if not regwin:
+            emit_release()
+        e("++unit;")
+        e.close()
+    e.close()   # while
+    e.close()   # kernel
+    return e.text()
+
+
+def _const_index(index):
+    if isinstance(index, pp.Const):
+        return int(index.value)
+    if isinstance(index, pp.Cast) and isinstance(index.operand, pp.Const):
+        return int(index.operand.value)
+    return None
+
+
+def make_plan(program, domain, device_props, options, override=None):
+    from .transformer import CudaPlan
+    from .planner import Launch
+    cfg = choose_config(program, domain, device_props, override)
+    source = generate(program, domain, cfg)
+    rank = cfg.rank
+    shape = program.shape
+    specs = []
+    for arg in _grid_args(program):
+        if rank == 3:
+            n0, n1, n2 = shape
+            specs.append(TensorMapSpec(arg.index, (n2, n1, n0), (n2 * 4, n1 * n2 * 4),
+                                       (cfg.PITCH, cfg.ROWS, 1), tag="tile"))
+        else:
+            n0, n1 = shape
+            specs.append(TensorMapSpec(arg.index, (n1, n0), (n1 * 4,), (cfg.PITCH, cfg.U), tag="block"))
+    tiles_x = -(-shape[-1] // cfg.TX)
+    tiles_y = -(-shape[1] // cfg.TY) if rank == 3 else 1
+    slots = device_props.sm_count * cfg.blocks_per_sm
+    min_chunk = max(4 * cfg.W, 16) if rank == 3 else max(4 * cfg.U, 64)
+
+    def geometry(a0_begin, a0_end):
+        n_units = a0_end - a0_begin
+        chunks = plan_chunks(n_units, tiles_x * tiles_y, slots, cfg.W, min_chunk)
+        chunk_len = -(-n_units // chunks)
+        if rank == 2:
+            chunk_len = -(-chunk_len // cfg.U) * cfg.U if chunk_len > cfg.U else chunk_len
+        chunks = -(-n_units // chunk_len)
+        launch = Launch((tiles_x, tiles_y, chunks), (cfg.threads, 1, 1), cfg.smem_bytes)
+        launch.extra = (chunk_len,)
+        return launch
+
+    return CudaPlan(program, domain, 'stream', source, FUNCTION, options, geometry,
+                    tensor_maps=specs, notes={'config': cfg.describe()})

@@ -396,7 +396,10 @@ class ConcreteCudaStencil(object):
         values.append(ctypes.c_void_p(out_pointer))
         values.append(ctypes.c_int(a0_begin))
         values.append(ctypes.c_int(a0_end))
-        launch(self.module, plan.function, plan.geometry(a0_begin, a0_end), values,
+        geometry = plan.geometry(a0_begin, a0_end)
+        for extra in getattr(geometry, 'extra', ()):
+            values.append(ctypes.c_int(extra))
+        launch(self.module, plan.function, geometry, values,
                self.device.stream if stream is None else stream)
 
     # -- the call --------------------------------------------------------------------------------
