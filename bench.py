@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- GStencil/s of the stencil hot path on B200, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl cuda|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one sweep of the workload's stencil over its grid.
+
+Workloads (BASELINE.json configs):
+  laplacian512  C2  LaplacianKernel 7-point, 512^3 float32, clamp, single pass  (default at N=1)
+  jacobi3d      C5  Jacobi3D 2048x1024x1024 float32, clamp, slab-decomposed over N GPUs with halo
+                    exchange (default at N>1; strong scaling: the grid is fixed, slabs shrink)
+  simple1024    C1  SimpleKernel 3x3 Moore, 1024^2
+  conv5         C4  ConvolutionFilter 5x5, 16384^2, --boundary zero|clamp|copy|wrap
+  bilateral     C3  BetterBilateralFilter radius 9, 8192^2
+
+Keys: `value` = device-resident throughput (CUDA events around K launches, inputs in HBM);
+`e2e` = the same metric through the public API `stencil(numpy_array)` with pinned host buffers,
+host->device and device->host copies inside the timed region; `roofline` = algorithmic bytes
+(8 B/point) / kernel time against the measured HBM copy bandwidth; `cpu_baseline` = the restated
+reference OpenMP backend (oracle/, kind "port") on this host's cores.
+"""
+from __future__ import print_function
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+# ---- workloads --------------------------------------------------------------------------------------
+def make_workload(name, boundary, backend):
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    from stencil_code_b200.library.simple import SimpleKernel
+    from stencil_code_b200.library.convolution import ConvolutionFilter
+    from stencil_code_b200.library.better_bilateral_filter import BetterBilateralFilter
+    if name == "laplacian512":
+        return dict(label="C2 LaplacianKernel 7-point 512^3 float32 {} single pass".format(boundary or "clamp"),
+                    stencil=LaplacianKernel(backend=backend, boundary_handling=boundary or "clamp"),
+                    shape=(512, 512, 512), scale=1.0, cpu_variant="omp", cpu_shape=(512, 512, 512))
+    if name == "jacobi3d":
+        return dict(label="C5 Jacobi3D alpha=1 beta=0.25 2048x1024x1024 float32 {}".format(boundary or "clamp"),
+                    stencil=Jacobi3D(1.0, 0.25, backend=backend, boundary_handling=boundary or "clamp"),
+                    shape=(2048, 1024, 1024), scale=1.0, cpu_variant="omp", cpu_shape=(256, 1024, 1024))
+    if name == "simple1024":
+        return dict(label="C1 SimpleKernel 3x3 Moore 1024^2 float32 {}".format(boundary or "clamp"),
+                    stencil=SimpleKernel(backend=backend, boundary_handling=boundary or "clamp"),
+                    shape=(1024, 1024), scale=1000.0, cpu_variant="c_parallel", cpu_shape=(1024, 1024))
+    if name == "conv5":
+        kernel = numpy.ones((5, 5), numpy.int64)
+        kernel[2, 2] = -4
+        return dict(label="C4 ConvolutionFilter 5x5 16384^2 float32 {}".format(boundary or "copy"),
+                    stencil=ConvolutionFilter(convolution_array=kernel, backend=backend,
+                                              boundary_handling=boundary or "copy"),
+                    shape=(16384, 16384), scale=1.0, cpu_variant="c_parallel", cpu_shape=(4096, 16384))
+    if name == "bilateral":
+        return dict(label="C3 BetterBilateralFilter sigma_d=3 (radius 9) sigma_i=70 8192^2 float32 clamp",
+                    stencil=BetterBilateralFilter(3, 70, backend=backend),
+                    shape=(8192, 8192), scale=255.0, cpu_variant="c_parallel", cpu_shape=(512, 8192))
+    raise SystemExit("unknown workload " + name)
+
+
+def host_grid(shape, scale, seed=1):
+    rng = numpy.random.RandomState(seed)
+    grid = rng.random_sample(shape).astype(numpy.float32)
+    if scale != 1.0:
+        grid *= numpy.float32(scale)
+    return grid
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as handle:
+            return float(json.load(handle)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---- clocks ----------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.samples = []
+        self.process = None
+        self.device_index = device_index
+
+    def __enter__(self):
+        try:
+            self.process = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
+            self.thread = threading.Thread(target=self._read)
+            self.thread.daemon = True
+            self.thread.start()
+            time.sleep(0.15)
+        except Exception:
+            self.process = None
+        return self
+
+    def _read(self):
+        for line in self.process.stdout:
+            self.samples.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.process is not None:
+            time.sleep(0.1)
+            self.process.terminate()
+            try:
+                self.process.wait(timeout=2)
+            except Exception:
+                self.process.kill()
+
+    def summary(self):
+        clocks, maxima, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.samples:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                clocks.append(float(parts[0]))
+                maxima.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not clocks:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(c for c in clocks if c > 0.5 * max(clocks)) or sorted(clocks)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(maxima), "reasons": sorted(reasons),
+                "samples": len(clocks)}
+
+
+# ---- CPU legs --------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, steps, warmup):
+    """The restated reference OpenMP backend on this host's cores (oracle/, kind 'port')."""
+    from oracle.cref import ReferenceC, reference_args
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    stencil = workload["stencil"]
+    shape = workload["cpu_shape"]
+    grid = host_grid(shape, workload["scale"])
+    args = reference_args(stencil, (grid,))
+    variant = workload["cpu_variant"]
+    compiled = ReferenceC(stencil, args, variant)
+    for _ in range(max(1, warmup)):
+        compiled(*args)
+    times = []
+    for _ in range(steps):
+        compiled(*args)
+        times.append(compiled.last_seconds)
+    seconds = sum(times) / len(times)
+    points = float(numpy.prod(shape))
+    return {"value": points / seconds / 1e9, "unit": "GStencil/s", "cores": cores, "kind": "port",
+            "variant": variant,
+            "sample": "{} sweeps of {} ({} backend restated from the reference, gcc -O2 -std=c99 -fopenmp, "
+                      "OMP_NUM_THREADS={})".format(steps, "x".join(map(str, shape)), variant, cores),
+            "ms_per_sweep": seconds * 1e3}
+
+
+# ---- GPU legs ----------------------------------------------------------------------------------------------
+def run_single_gpu(args, workload):
+    from stencil_code_b200.backend.cuda import runtime
+    stencil = workload["stencil"]
+    shape = workload["shape"]
+    points = float(numpy.prod(shape))
+    device = runtime.Device.get(int(os.environ.get("LOCAL_RANK", "0")))
+    library = runtime.load_library()
+
+    # inputs: pinned host grid (same seed as the parity tests use), resident copy on the device
+    host_in = device.pinned_empty(shape, numpy.float32)
+    host_in[...] = host_grid(shape, workload["scale"])
+    call_args = (host_in,)
+    if hasattr(stencil, "intensity_lut"):
+        tables = (stencil.distance_lut, stencil.intensity_lut)
+    elif hasattr(stencil, "coefficients"):
+        tables = (stencil.coefficients,)
+    else:
+        tables = ()
+    concrete = stencil.specializer.specialize(call_args + tables)
+    plan = concrete.plan
+    stream = device.stream
+    buffers = [device.alloc(a.nbytes) for a in (host_in,) + tables]
+    out_buffer = device.alloc(host_in.nbytes)
+    for array, buffer in zip((host_in,) + tables, buffers):
+        array = numpy.ascontiguousarray(array)
+        runtime.check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(array.ctypes.data),
+                                                  array.nbytes, stream))
+    device.synchronize(stream)
+    pointers = [b.ptr for b in buffers]
+
+    def sweep():
+        concrete.launch(pointers, out_buffer.ptr, stream=stream)
+
+    for _ in range(max(3, args.warmup)):
+        sweep()
+    device.synchronize(stream)
+    start, stop = device.new_event(True), device.new_event(True)
+    with ClockSampler(device.index) as clocks:
+        runtime.check(library.sc_event_record(start, stream))
+        for _ in range(args.steps):
+            sweep()
+        runtime.check(library.sc_event_record(stop, stream))
+        device.synchronize(stream)
+    elapsed = ctypes.c_float()
+    runtime.check(library.sc_event_elapsed_ms(start, stop, ctypes.byref(elapsed)))
+    ms_per_step = elapsed.value / args.steps
+    value = points / (ms_per_step * 1e-3) / 1e9
+
+    # end to end through the public API: numpy (pinned) in, numpy out, copies inside the timed region
+    e2e_steps = max(3, min(args.steps, 10))
+    result = None
+    for _ in range(2):
+        result = stencil(host_in)
+    begin = time.perf_counter()
+    for _ in range(e2e_steps):
+        result = stencil(host_in)
+    e2e_seconds = (time.perf_counter() - begin) / e2e_steps
+    checksum = float(result.ravel()[:: max(1, result.size // 4096)].sum())
+
+    peak, peak_source = hbm_peak()
+    achieved = 8.0 * points / (ms_per_step * 1e-3) / 1e9
+    info = concrete.module.function_info(plan.function)
+    geometry = plan.geometry(*plan.domain.sweep_range)
+    line = {
+        "metric": "GStencil/s", "value": value, "unit": "GStencil/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (numpy RandomState(1) uniform)",
+        "config": {"workload": workload["label"], "strategy": plan.strategy,
+                   "l2": "grid in+out = {:.0f} MiB, larger than the 126 MiB L2 (no flush needed)".format(
+                       2 * host_in.nbytes / 2 ** 20) if 2 * host_in.nbytes > 2 * 126 * 2 ** 20 else
+                   "grid fits in L2: L2-resident, launch-latency bound",
+                   "kernel": dict(plan.notes.get("config", {}), grid=list(geometry.grid), block=list(geometry.block),
+                                  regs=info["regs"], spill_bytes=info["local_bytes"])},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_source,
+                     "algorithmic_bytes_per_launch": 8.0 * points},
+        "e2e": {"value": points / e2e_seconds / 1e9, "unit": "GStencil/s", "ms_per_step": e2e_seconds * 1e3,
+                "h2d_bytes_per_step": int(host_in.nbytes + sum(numpy.asarray(t).nbytes for t in tables)),
+                "d2h_bytes_per_step": int(host_in.nbytes), "checksum": checksum},
+        "gpu_launches": args.steps,
+        "clocks": clocks.summary(),
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_reference_run(make_workload(args.workload, args.boundary, "python"),
+                                                 steps=3, warmup=1)
+    return line
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=20)
+    parser.add_argument("--warmup", type=int, default=5)
+    parser.add_argument("--workload", default=None)
+    parser.add_argument("--boundary", default=None)
+    parser.add_argument("--impl", default="cuda", choices=("cuda", "reference"))
+    parser.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = parser.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.workload is None:
+        args.workload = "laplacian512" if args.gpus == 1 else "jacobi3d"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        workload = make_workload(args.workload, args.boundary, "python")
+        base = cpu_reference_run(workload, steps=args.steps, warmup=args.warmup)
+        line = {"impl": "reference", "metric": "GStencil/s", "value": base["value"], "unit": "GStencil/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": base["ms_per_sweep"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic (numpy RandomState(1) uniform)",
+                "config": {"workload": workload["label"], "cpu_grid": list(workload["cpu_shape"])},
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "GStencil/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if args.gpus > 1 or world > 1:
+        from stencil_code_b200.backend.cuda import multi_gpu_bench
+        line = multi_gpu_bench.run(args, make_workload(args.workload, args.boundary, "cuda"))
+        if line is not None:
+            print(json.dumps(line))
+        return
+    print(json.dumps(run_single_gpu(args, make_workload(args.workload, args.boundary, "cuda"))))
+
+
+if __name__ == "__main__":
+    main()

@@ -105,7 +105,7 @@ int         sc_function_occupancy(sc_module* module, const char* function,
 /* ---- TMA descriptor ------------------------------------------------------------------------ */
 /* dtype: 0 = float32, 1 = float64, 2 = int32, 3 = uint8.  dims / box are innermost-first
  * (dims[0] is the contiguous axis); strides_bytes has rank-1 entries (dims 1..rank-1).
- * oob_fill: 0 = zeros.  interleave none, swizzle none, L2 promotion 256 B.                     */
+ * oob_fill: 0 = zeros.  interleave none, swizzle none, L2 promotion 128 B.                     */
 int         sc_tensormap_tiled(sc_tmap* out, void* global_address, int dtype, int rank,
                                const uint64_t* dims, const uint64_t* strides_bytes,
                                const uint32_t* box, int oob_fill);

@@ -187,19 +187,34 @@ def choose_config(program, domain, device_props, override=None):
     copy_center = program.boundary == 'copy'
     n_fast = program.shape[-1]
     n_grids = len(_grid_args(program))
-    override = override or {}
+    override = dict(override or {})
+    # tuning knob: STENCIL_CUDA_STREAM="TY=64,BY=4,NCW=16,prefetch=2" forces tile parameters
+    import os
+    for item in filter(None, os.environ.get("STENCIL_CUDA_STREAM", "").split(",")):
+        key, _, value = item.partition("=")
+        override[key.strip()] = value.strip() if key.strip() == 'mode' else int(value)
 
     candidates = []
     if rank == 3:
-        for TY, BY, NCW in ((32, 4, 8), (16, 4, 4), (32, 2, 16), (16, 2, 8), (8, 2, 4), (8, 1, 8)):
-            candidates.append(dict(TX=128, TY=TY, BY=BY, NCW=NCW, U=1))
+        for TY, BY, NCW, prefetch in ((64, 4, 16, 3), (32, 4, 8, 2), (32, 4, 8, 3), (16, 4, 4, 3),
+                                      (32, 2, 16, 3), (16, 2, 8, 3), (8, 2, 4, 3), (8, 1, 8, 3)):
+            candidates.append(dict(TX=128, TY=TY, BY=BY, NCW=NCW, U=1, prefetch=prefetch))
     else:
         # rank 2: every consumer warp owns a 128-column sub-tile with its own TMA box and halo
         for NCW, U in ((4, 8), (8, 8), (4, 16), (2, 16), (2, 8), (1, 16), (1, 8)):
-            candidates.append(dict(TX=NCW * 128, TY=1, BY=1, NCW=NCW, U=U))
+            candidates.append(dict(TX=NCW * 128, TY=1, BY=1, NCW=NCW, U=U, prefetch=2))
     best = None
+    if any(k in override for k in ('TY', 'BY', 'NCW', 'U')):
+        forced = dict(candidates[0])
+        forced.update({k: v for k, v in override.items() if k in forced})
+        if rank == 2:
+            forced['TX'] = forced['NCW'] * 128
+        candidates = [forced]
+    elif 'prefetch' in override:
+        for cand in candidates:
+            cand['prefetch'] = override['prefetch']
+    n_stream = domain.sweep_range[1] - domain.sweep_range[0]
     for cand in candidates:
-        cand.update({k: v for k, v in override.items() if k in cand})
         fp = Footprint(program, cand['BY'], copy_center)
         mode = override.get('mode') or ('regwin' if fp.window_registers <= 160 else 'smem')
         W = fp.window
@@ -211,8 +226,7 @@ def choose_config(program, domain, device_props, override=None):
         if rank == 2 and U <= max(-fp.hz_lo, fp.hz_hi):
             continue
         resident_stages = (resident_units + U - 1) // U + (1 if U > 1 else 0)
-        prefetch = override.get('prefetch', 3 if rank == 3 else 2)
-        S = resident_stages + prefetch
+        S = resident_stages + cand['prefetch']
         pitch = 128 + 2 * PADX
         if pitch > 256:
             continue
@@ -229,25 +243,36 @@ def choose_config(program, domain, device_props, override=None):
                             device_props.max_threads_per_sm // threads, 8)
         if blocks_per_sm < 1:
             continue
-        # wider tiles than the grid waste lanes; prefer the tile that wastes least, then the one
-        # with the smallest halo overhead, then more resident warps
-        waste_x = (-(-n_fast // cand['TX']) * cand['TX']) / float(n_fast)
-        waste_y = 1.0
-        halo = 1.0
+        # cost model: DRAM traffic per useful byte (halo rows, 32-byte sectors of the column pad,
+        # window start-up per chunk; L2 does not absorb the overlap -- measured, profiles/) divided
+        # by how well tiles x chunks fill whole waves of resident CTAs, with lanes wasted on
+        # partial tiles counted as extra work
+        tiles_x = -(-n_fast // cand['TX'])
+        waste = tiles_x * cand['TX'] / float(n_fast)
+        tiles = tiles_x
+        read_factor = (128 * 4 + (64 if PADX else 0)) / 512.0
         if rank == 3:
             n_rows = program.shape[1]
-            waste_y = (-(-n_rows // cand['TY']) * cand['TY']) / float(n_rows)
-            halo = (cand['TY'] + 2 * hy) * pitch / float(cand['TY'] * cand['TX'])
-        else:
-            halo = pitch / 128.0
+            tiles_y = -(-n_rows // cand['TY'])
+            tiles *= tiles_y
+            waste *= tiles_y * cand['TY'] / float(n_rows)
+            read_factor *= (cand['TY'] + 2 * hy) / float(cand['TY'])
+        slots = device_props.sm_count * blocks_per_sm
+        min_chunk = max(4 * W, 16) if rank == 3 else max(4 * U, 64)
+        chunks = plan_chunks(n_stream, tiles, slots, W, min_chunk)
+        chunk_len = -(-n_stream // chunks)
+        read_factor *= (chunk_len + W - 1) / float(chunk_len)
+        items = tiles * (-(-n_stream // chunk_len))
+        fill = items / float(-(-items // slots) * slots)
         resident_warps = blocks_per_sm * cand['NCW']
-        score = (waste_x * waste_y * halo) * (1.0 if resident_warps >= 12 else 1.15)
+        score = waste * (1.0 + read_factor) / 2.0 / fill * (1.0 if resident_warps >= 12 else 1.1)
         config = StreamConfig(rank=rank, PADX=PADX, HX=hx, HY=hy, HZ_LO=fp.hz_lo, HZ_HI=fp.hz_hi, W=W,
                               mode=mode, S=S, PITCH=pitch, ROWS=rows, STAGE_FLOATS=stage_bytes_aligned // 4,
                               STAGE_BYTES=stage_bytes, smem_bytes=smem, threads=threads, NSUB=n_sub,
                               SUB_FLOATS=rows * pitch,
                               blocks_per_sm=blocks_per_sm, footprint=fp, n_grids=n_grids,
-                              score=score, **cand)
+                              score=score, TX=cand['TX'], TY=cand['TY'], BY=cand['BY'], NCW=cand['NCW'],
+                              U=cand['U'])
         if best is None or score < best.score - 1e-9:
             best = config
     if best is None:

@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -476,10 +477,20 @@ int sc_tensormap_tiled(sc_tmap* out, void* global_address, int dtype, int rank,
             global_strides[i] = strides_bytes[i];
         }
     }
+    // L2 promotion: 128 B by default; STENCIL_CUDA_L2_PROMOTION=0|64|128|256 overrides (tuning knob)
+    CUtensorMapL2promotion promotion = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char* env = getenv("STENCIL_CUDA_L2_PROMOTION")) {
+        switch (atoi(env)) {
+            case 0: promotion = CU_TENSOR_MAP_L2_PROMOTION_NONE; break;
+            case 64: promotion = CU_TENSOR_MAP_L2_PROMOTION_L2_64B; break;
+            case 256: promotion = CU_TENSOR_MAP_L2_PROMOTION_L2_256B; break;
+            default: promotion = CU_TENSOR_MAP_L2_PROMOTION_L2_128B; break;
+        }
+    }
     CUresult rc = g_drv.cuTensorMapEncodeTiled_(
         reinterpret_cast<CUtensorMap*>(out), type, (cuuint32_t)rank, global_address, global_dims,
         global_strides, box_dims, element_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
-        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_SWIZZLE_NONE, promotion,
         oob_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return cuda_fail(rc, "cuTensorMapEncodeTiled");
     return SC_OK;
