@@ -122,6 +122,11 @@ int         sc_stream_create(void** stream);
 int         sc_stream_destroy(void* stream);
 int         sc_stream_synchronize(void* stream);
 int         sc_stream_wait_event(void* stream, void* event);
+/* stream-ordered flag operations on a 32-bit word in device memory: the stream blocks until
+ * *device_ptr >= value (wait), or sets *device_ptr = value once prior work is done (write).  Used
+ * with flags that a neighbouring rank's kernel writes through peer memory.                       */
+int         sc_stream_wait_value32(void* stream, void* device_ptr, uint32_t value);
+int         sc_stream_write_value32(void* stream, void* device_ptr, uint32_t value);
 int         sc_event_create(void** event, int with_timing);
 int         sc_event_destroy(void* event);
 int         sc_event_record(void* event, void* stream);

@@ -54,6 +54,8 @@ def generate(program, domain):
     for arg in program.args:
         params.append("const {}* __restrict__ a{}".format(arg.ctype, arg.index))
     params.append("{}* __restrict__ out".format(program.out_ctype))
+    params.append("{}* __restrict__ out_peer".format(program.out_ctype))   # neighbour slab's ghost planes (or NULL)
+    params.append("i64 peer_shift")                                        # element offset into out_peer
     params.append("int a0_begin")
     params.append("int a0_end")
 
@@ -92,10 +94,12 @@ def generate(program, domain):
             halo_value = "a0[idx]" if program.boundary == 'copy' else ctype_zero(program.out_ctype)
             if program.boundary == 'copy' and program.args[0].ctype != program.out_ctype:
                 halo_value = "({}){}".format(program.out_ctype, halo_value)
-            lines.append("    if ({}) {{ out[idx] = {}; return; }}".format(" || ".join(tests), halo_value))
+            lines.append("    if ({}) {{ out[idx] = {}; if (out_peer) out_peer[idx + peer_shift] = {}; return; }}".format(
+                " || ".join(tests), halo_value, halo_value))
     lines.append("    {} acc = {};".format(program.out_ctype, ctype_zero(program.out_ctype)))
     lines.extend(emit_statements(program, tap_text, table_text))
     lines.append("    out[idx] = acc;")
+    lines.append("    if (out_peer) out_peer[idx + peer_shift] = acc;")
     lines.append("}")
     return "\n".join(lines) + "\n"
 

@@ -401,7 +401,8 @@ def generate(program, domain, cfg):
     params = ["const {}* __restrict__ a{}".format(arg.ctype, arg.index) for arg in program.args]
     for arg in grids:
         params.append("const __grid_constant__ TensorMap tm{}".format(arg.index))
-    params += ["float* __restrict__ out", "int a0_begin", "int a0_end", "int chunk_len"]
+    params += ["float* __restrict__ out", "float* __restrict__ out_peer", "i64 peer_shift",
+               "int a0_begin", "int a0_end", "int chunk_len"]
     e('extern "C" __global__ void __launch_bounds__({}, {})'.format(cfg.threads, cfg.blocks_per_sm))
     e("{}({})".format(FUNCTION, ", ".join(params)))
     e.open("")
@@ -709,7 +710,11 @@ def generate(program, domain, cfg):
             else:
                 cond = "col_ok"
                 address = "out + (i64)z * {} + gx".format(N2)
-            e("if ({}) st_global_v4({}, {});".format(cond, address, ", ".join(acc[b])))
+            e.open("if ({})".format(cond))
+            e("float* const dst = {};".format(address))
+            e("st_global_v4(dst, {});".format(", ".join(acc[b])))
+            e("if (out_peer) st_global_v4(out_peer + (dst - out) + peer_shift, {});".format(", ".join(acc[b])))
+            e.close()
         e.close()   # if unit >= W-1
         if not regwin:
             emit_release()

@@ -1,0 +1,262 @@
+"""Slab-decomposed iterated stencils across the GPUs of one box.
+
+The reference has no multi-device path at all; this is the north-star's addition for iterated
+sweeps (Jacobi-3D).  One process per GPU.  The global grid is cut along axis 0 into contiguous
+slabs; every rank's local array carries ``h`` ghost planes on both sides (``h`` = ghost depth along
+axis 0).  A sweep on one rank is three launches of the SAME generated kernel over axis-0
+sub-ranges, all on one stream:
+
+  1. top boundary planes    -> local result AND, through a peer-mapped pointer, straight into the
+  2. bottom boundary planes    neighbour's ghost planes (NVLink stores issued by the stencil kernel
+                               itself: no pack/copy/unpack, no NCCL in the data path)
+  3. ``sc_signal``: system-scope fence + flag store (sweep number) into each neighbour's memory
+  4. interior planes (the bulk; overlaps the neighbours' progress)
+
+and the next sweep starts with a stream-ordered wait (``sc_stream_wait_value32``) until both
+neighbours' flags reached the previous sweep number.  Interior planes never read ghost planes, so
+a neighbour can never overwrite ghosts that are still being read (see ``iterate``).
+
+``torch.distributed`` is used for the plumbing only: exchanging CUDA IPC handles, barriers and the
+final reductions.  Results are bit-identical to the single-GPU sweep: the per-point arithmetic is
+the same generated code, only ``Domain`` (open faces) differs.
+"""
+import ctypes
+
+import numpy
+
+from ...stencil_exception import StencilException
+
+
+class SlabDecomposition(object):
+    """Pure host arithmetic of the axis-0 slab cut (unit-tested on CPU with gloo)."""
+
+    def __init__(self, global_shape, ghost0, world, rank):
+        self.global_shape = tuple(int(s) for s in global_shape)
+        self.h = int(ghost0)
+        self.world, self.rank = int(world), int(rank)
+        n0 = self.global_shape[0]
+        if self.world < 1 or not (0 <= self.rank < self.world):
+            raise StencilException("bad rank {} of {}".format(rank, world))
+        base, extra = divmod(n0, self.world)
+        counts = [base + (1 if r < extra else 0) for r in range(self.world)]
+        if min(counts) < max(1, 2 * self.h):
+            raise StencilException("{} planes over {} ranks leaves slabs thinner than twice the "
+                                   "ghost depth {}".format(n0, world, self.h))
+        self.counts = counts
+        self.starts = [sum(counts[:r]) for r in range(self.world)]
+        self.start = self.starts[self.rank]
+        self.planes = counts[self.rank]
+        self.stop = self.start + self.planes
+        self.open_lo = self.world > 1 and self.rank > 0
+        self.open_hi = self.world > 1 and self.rank < self.world - 1
+        self.ghosted = self.world > 1
+        pad = 2 * self.h if self.ghosted else 0
+        self.local_shape = (self.planes + pad,) + self.global_shape[1:]
+        self.plane_elems = int(numpy.prod(self.global_shape[1:], dtype=numpy.int64)) if len(self.global_shape) > 1 else 1
+
+    @property
+    def first_real(self):
+        """local axis-0 index of this rank's first real plane"""
+        return self.h if self.ghosted else 0
+
+    def local_index(self, global_plane):
+        return global_plane - self.start + self.first_real
+
+    def ranges(self):
+        """(top, interior, bottom) local axis-0 ranges of one sweep; top/bottom are the planes a
+        neighbour needs (and the only ones that read ghost planes)."""
+        lo, hi = self.first_real, self.first_real + self.planes
+        top = (lo, min(lo + self.h, hi)) if self.open_lo else (lo, lo)
+        bottom = (max(hi - self.h, top[1]), hi) if self.open_hi else (hi, hi)
+        return top, (top[1], bottom[0]), bottom
+
+    def sends(self):
+        """[(neighbour rank, local source range, neighbour's local destination range)]"""
+        plan = []
+        lo, hi = self.first_real, self.first_real + self.planes
+        if self.open_lo:
+            up_planes = self.counts[self.rank - 1]
+            plan.append((self.rank - 1, (lo, lo + self.h), (self.h + up_planes, 2 * self.h + up_planes)))
+        if self.open_hi:
+            plan.append((self.rank + 1, (hi - self.h, hi), (0, self.h)))
+        return plan
+
+
+class SlabStencil(object):
+    """An iterated stencil on this rank's slab, exchanging ghost planes through peer memory."""
+
+    def __init__(self, stencil, global_shape, tables=(), world=None, rank=None, device_index=None):
+        import torch.distributed as dist
+        from . import runtime
+        self.dist = dist
+        self.runtime = runtime
+        if world is None:
+            world = dist.get_world_size() if dist.is_initialized() else 1
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        self.stencil = stencil
+        self.slab = SlabDecomposition(global_shape, stencil.ghost_depth[0], world, rank)
+        self.device = runtime.Device.get(device_index)
+        self.library = runtime.load_library()
+        self.tables = [numpy.ascontiguousarray(t) for t in tables]
+        slab = self.slab
+
+        class _Shape(object):
+            def __init__(self, shape, dtype):
+                self.shape, self.dtype = shape, numpy.dtype(dtype)
+        fake_args = (_Shape(slab.local_shape, numpy.float32),) + tuple(self.tables)
+        self.concrete = stencil.specializer.specialize(fake_args, open_faces=(slab.open_lo, slab.open_hi))
+        self.nbytes = int(numpy.prod(slab.local_shape, dtype=numpy.int64)) * 4
+        self.buffers = [self.device.alloc(self.nbytes), self.device.alloc(self.nbytes)]
+        self.flags = self.device.alloc(256)
+        runtime.check(self.library.sc_memset32_async(ctypes.c_void_p(self.flags.ptr), 0, 64, self.device.stream))
+        self.table_buffers = []
+        for table in self.tables:
+            buffer = self.device.alloc(table.nbytes)
+            runtime.check(self.library.sc_memcpy_h2d_async(
+                ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(table.ctypes.data), table.nbytes, self.device.stream))
+            self.table_buffers.append(buffer)
+        self.device.synchronize()
+        self.sweep = 0
+        self.peers = {}
+        if slab.ghosted:
+            self._open_peers()
+
+    # -- setup -----------------------------------------------------------------------------------
+    def _handle(self, pointer):
+        raw = ctypes.create_string_buffer(64)
+        self.runtime.check(self.library.sc_ipc_get_mem_handle(ctypes.c_void_p(pointer), raw))
+        return raw.raw
+
+    def _open(self, handle):
+        pointer = ctypes.c_void_p()
+        self.runtime.check(self.library.sc_ipc_open_mem_handle(handle, ctypes.byref(pointer)), "peer mapping")
+        return pointer.value
+
+    def _open_peers(self):
+        mine = {"rank": self.slab.rank, "buffers": [self._handle(b.ptr) for b in self.buffers],
+                "flags": self._handle(self.flags.ptr)}
+        everyone = [None] * self.slab.world
+        self.dist.all_gather_object(everyone, mine)
+        for neighbour in (self.slab.rank - 1, self.slab.rank + 1):
+            if 0 <= neighbour < self.slab.world:
+                info = everyone[neighbour]
+                self.peers[neighbour] = {"buffers": [self._open(h) for h in info["buffers"]],
+                                         "flags": self._open(info["flags"])}
+        self.dist.barrier()
+
+    def close(self):
+        for peer in self.peers.values():
+            for pointer in peer["buffers"] + [peer["flags"]]:
+                self.library.sc_ipc_close_mem_handle(ctypes.c_void_p(pointer))
+        self.peers = {}
+
+    # -- data in / out ----------------------------------------------------------------------------
+    def _current(self):
+        return self.buffers[self.sweep % 2]
+
+    def fill_uniform(self, seed=1, scale=1.0):
+        """Counter-based uniform [0, scale) fill, a function of the GLOBAL element index, so every
+        decomposition of the same grid holds the same values (ghost planes included)."""
+        slab = self.slab
+        first_global = slab.start - slab.first_real            # global plane of local plane 0
+        count = int(numpy.prod(slab.local_shape, dtype=numpy.int64))
+        offset = first_global * slab.plane_elems               # may be negative on rank 0: wraps, unused
+        geometry = type("L", (), dict(grid=(148 * 8, 1, 1), block=(256, 1, 1), cluster=(1, 1, 1), smem=0))()
+        self.runtime.launch(self.device.utils(), "sc_fill_uniform", geometry,
+                            [ctypes.c_void_p(self._current().ptr), ctypes.c_uint64(count), ctypes.c_uint64(seed),
+                             ctypes.c_uint64(offset % (1 << 64)), ctypes.c_float(scale)], self.device.stream)
+        self.device.synchronize()
+        if slab.ghosted:
+            self.dist.barrier()
+
+    def load(self, global_grid):
+        """Copy this rank's planes (plus ghost planes) of a host array of the global shape."""
+        slab = self.slab
+        lo = max(0, slab.start - slab.first_real)
+        hi = min(slab.global_shape[0], slab.stop + (slab.h if slab.ghosted else 0))
+        part = numpy.ascontiguousarray(global_grid[lo:hi], dtype=numpy.float32)
+        local_lo = lo - (slab.start - slab.first_real)
+        destination = self._current().ptr + local_lo * slab.plane_elems * 4
+        self.runtime.check(self.library.sc_memcpy_h2d_async(
+            ctypes.c_void_p(destination), ctypes.c_void_p(part.ctypes.data), part.nbytes, self.device.stream))
+        self.device.synchronize()
+        if slab.ghosted:
+            self.dist.barrier()
+
+    def result(self):
+        """This rank's real planes as a host array."""
+        slab = self.slab
+        shape = (slab.planes,) + slab.global_shape[1:]
+        out = self.device.pinned_empty(shape, numpy.float32)
+        source = self._current().ptr + slab.first_real * slab.plane_elems * 4
+        self.runtime.check(self.library.sc_memcpy_d2h_async(
+            ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(source), out.nbytes, self.device.stream))
+        self.device.synchronize()
+        return out
+
+    def checksum(self):
+        """Position-dependent 64-bit checksum of the real planes; summed (mod 2^64) over ranks it
+        is independent of the decomposition."""
+        slab = self.slab
+        count = slab.planes * slab.plane_elems
+        cell = self.device.alloc(256)
+        self.runtime.check(self.library.sc_memset32_async(ctypes.c_void_p(cell.ptr), 0, 2, self.device.stream))
+        geometry = type("L", (), dict(grid=(148 * 8, 1, 1), block=(256, 1, 1), cluster=(1, 1, 1), smem=0))()
+        source = self._current().ptr + slab.first_real * slab.plane_elems * 4
+        self.runtime.launch(self.device.utils(), "sc_checksum", geometry,
+                            [ctypes.c_void_p(source), ctypes.c_uint64(count),
+                             ctypes.c_uint64(slab.start * slab.plane_elems), ctypes.c_void_p(cell.ptr)],
+                            self.device.stream)
+        host = numpy.zeros(1, numpy.uint64)
+        self.runtime.check(self.library.sc_memcpy_d2h_async(
+            ctypes.c_void_p(host.ctypes.data), ctypes.c_void_p(cell.ptr), 8, self.device.stream))
+        self.device.synchronize()
+        cell.release()
+        value = int(host[0])
+        if slab.ghosted:
+            parts = [None] * slab.world
+            self.dist.all_gather_object(parts, value)
+            value = sum(parts) % (1 << 64)
+        return value
+
+    # -- sweeps ------------------------------------------------------------------------------------
+    def iterate(self, sweeps):
+        """Enqueue ``sweeps`` sweeps on this rank's stream (asynchronous; see ``synchronize``)."""
+        slab = self.slab
+        runtime, library, stream = self.runtime, self.library, self.device.stream
+        tables = [b.ptr for b in self.table_buffers]
+        top, interior, bottom = slab.ranges()
+        up, down = self.peers.get(slab.rank - 1), self.peers.get(slab.rank + 1)
+        plane = slab.plane_elems
+        signal_geometry = type("L", (), dict(grid=(1, 1, 1), block=(32, 1, 1), cluster=(1, 1, 1), smem=0))()
+        for _ in range(sweeps):
+            number = self.sweep + 1
+            current = self.buffers[self.sweep % 2].ptr
+            target_index = (self.sweep + 1) % 2
+            target = self.buffers[target_index].ptr
+            # ghost planes of `current` were written by the neighbours during sweep number-1
+            # (initial ghosts come from load()/fill_uniform()).  Flags: [0] from up, [1] from down.
+            if number > 1:
+                if up:
+                    runtime.check(library.sc_stream_wait_value32(stream, ctypes.c_void_p(self.flags.ptr), number - 1))
+                if down:
+                    runtime.check(library.sc_stream_wait_value32(stream, ctypes.c_void_p(self.flags.ptr + 4), number - 1))
+            if up:
+                # my first h real planes become the upper neighbour's lower ghost planes
+                shift = slab.counts[slab.rank - 1] * plane
+                self.concrete.launch([current] + tables, target, top[0], top[1], stream,
+                                     peer_pointer=up["buffers"][target_index], peer_shift=shift)
+            if down:
+                shift = -slab.planes * plane
+                self.concrete.launch([current] + tables, target, bottom[0], bottom[1], stream,
+                                     peer_pointer=down["buffers"][target_index], peer_shift=shift)
+            if up or down:
+                runtime.launch(self.device.utils(), "sc_signal", signal_geometry,
+                               [ctypes.c_void_p(up["flags"] + 4 if up else 0),
+                                ctypes.c_void_p(down["flags"] if down else 0),
+                                ctypes.c_uint32(number)], stream)
+            self.concrete.launch([current] + tables, target, interior[0], interior[1], stream)
+            self.sweep += 1
+
+    def synchronize(self):
+        self.device.synchronize(self.device.stream)

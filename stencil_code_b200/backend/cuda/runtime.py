@@ -88,6 +88,8 @@ SYMBOLS = {
     "sc_host_free": (_I, [_VP]),
     "sc_host_register": (_I, [_VP, _SZ]),
     "sc_host_unregister": (_I, [_VP]),
+    "sc_stream_wait_value32": (_I, [_VP, _VP, ctypes.c_uint32]),
+    "sc_stream_write_value32": (_I, [_VP, _VP, ctypes.c_uint32]),
     "sc_ipc_get_mem_handle": (_I, [_VP, ctypes.c_char_p]),
     "sc_ipc_open_mem_handle": (_I, [ctypes.c_char_p, _PVP]),
     "sc_ipc_close_mem_handle": (_I, [_VP]),
@@ -380,8 +382,11 @@ class ConcreteCudaStencil(object):
             self._tmaps[key] = tmap
         return tmap
 
-    def launch(self, arg_pointers, out_pointer, a0_begin=None, a0_end=None, stream=None):
-        """Enqueue the stencil over axis-0 range [a0_begin, a0_end) on ``stream``."""
+    def launch(self, arg_pointers, out_pointer, a0_begin=None, a0_end=None, stream=None,
+               peer_pointer=0, peer_shift=0):
+        """Enqueue the stencil over axis-0 range [a0_begin, a0_end) on ``stream``.  With
+        ``peer_pointer`` every result is also stored at ``peer_pointer[flat_index + peer_shift]``
+        (a neighbouring slab's ghost planes, mapped peer memory)."""
         plan = self.plan
         lo, hi = plan.domain.sweep_range
         a0_begin = lo if a0_begin is None else a0_begin
@@ -394,6 +399,8 @@ class ConcreteCudaStencil(object):
         for spec in plan.tensor_maps:
             values.append(self._tensor_map(spec, arg_pointers[spec.arg]))
         values.append(ctypes.c_void_p(out_pointer))
+        values.append(ctypes.c_void_p(peer_pointer))
+        values.append(ctypes.c_longlong(peer_shift))
         values.append(ctypes.c_int(a0_begin))
         values.append(ctypes.c_int(a0_end))
         geometry = plan.geometry(a0_begin, a0_end)

@@ -8,6 +8,8 @@
 //   sc_checksum       order-independent 64-bit checksum of a float32 grid (bit patterns), used to
 //                     compare 1-GPU and k-GPU results at sizes no CPU oracle can reach
 //   sc_count_diff     number of elements whose bit patterns differ between two grids
+//   sc_signal         publish "my boundary planes for sweep `value` are in your ghost planes":
+//                     system-scope fence, then a flag store into the neighbour's (peer-mapped) memory
 typedef unsigned int u32;
 typedef unsigned long long u64;
 
@@ -53,4 +55,13 @@ sc_count_diff(const u32* __restrict__ a, const u32* __restrict__ b, u64 count, u
     for (int offset = 16; offset > 0; offset >>= 1)
         local += __shfl_xor_sync(0xffffffffu, local, offset);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(result, local);
+}
+
+extern "C" __global__ void sc_signal(volatile u32* flag_a, volatile u32* flag_b, u32 value) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        __threadfence_system();
+        if (flag_a) *flag_a = value;
+        if (flag_b) *flag_b = value;
+        __threadfence_system();
+    }
 }

@@ -46,7 +46,7 @@ int fail(int code, const char* fmt, ...) {
     X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction) X(cuFuncGetAttribute) \
     X(cuFuncSetAttribute) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuLaunchKernelEx) \
     X(cuTensorMapEncodeTiled) \
-    X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent) \
+    X(cuStreamWaitValue32) X(cuStreamWriteValue32) X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent) \
     X(cuEventCreate) X(cuEventDestroy) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) \
     X(cuMemAlloc) X(cuMemFree) X(cuMemsetD32Async) X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) \
     X(cuMemcpyDtoDAsync) X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostRegister) \
@@ -552,6 +552,20 @@ int sc_stream_synchronize(void* stream) {
 int sc_stream_wait_event(void* stream, void* event) {
     NEED_CONTEXT();
     CU(cuStreamWaitEvent_(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUevent>(event), 0));
+    return SC_OK;
+}
+
+int sc_stream_wait_value32(void* stream, void* device_ptr, uint32_t value) {
+    NEED_CONTEXT();
+    CU(cuStreamWaitValue32_(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(device_ptr),
+                            value, CU_STREAM_WAIT_VALUE_GEQ));
+    return SC_OK;
+}
+
+int sc_stream_write_value32(void* stream, void* device_ptr, uint32_t value) {
+    NEED_CONTEXT();
+    CU(cuStreamWriteValue32_(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(device_ptr),
+                             value, CU_STREAM_WRITE_VALUE_DEFAULT));
     return SC_OK;
 }
 

@@ -1,0 +1,107 @@
+"""Slab decomposition: host logic on CPU with gloo (world_size 2 and 3), device path on >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import numpy
+import pytest
+
+from stencil_code_b200.backend.cuda.multi_gpu import SlabDecomposition
+from stencil_code_b200.stencil_exception import StencilException
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_decomposition_arithmetic():
+    parts = [SlabDecomposition((50, 8, 8), 1, 4, r) for r in range(4)]
+    assert [p.planes for p in parts] == [13, 13, 12, 12]
+    assert [p.start for p in parts] == [0, 13, 26, 38] and parts[-1].stop == 50
+    assert parts[0].local_shape == (15, 8, 8) and not parts[0].open_lo and parts[0].open_hi
+    top, interior, bottom = parts[1].ranges()
+    assert top == (1, 2) and interior == (2, 13) and bottom == (13, 14)
+    top, interior, bottom = parts[0].ranges()
+    assert top == (1, 1) and interior == (1, 13) and bottom == (13, 14)     # global top: no exchange
+    assert parts[1].sends() == [(0, (1, 2), (14, 15)), (2, (13, 14), (0, 1))]
+    single = SlabDecomposition((50, 8, 8), 1, 1, 0)
+    assert single.local_shape == (50, 8, 8) and single.ranges() == ((0, 0), (0, 50), (50, 50))
+    with pytest.raises(StencilException):
+        SlabDecomposition((6, 8, 8), 2, 4, 0)
+
+
+WORKER = r'''
+import os, sys
+import numpy
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import torch, torch.distributed as dist
+from stencil_code_b200.backend.cuda.multi_gpu import SlabDecomposition
+from stencil_code_b200.library.jacobi_3d import Jacobi3D
+from oracle.cref import reference_c
+
+dist.init_process_group("gloo")
+world, rank = dist.get_world_size(), dist.get_rank()
+shape, sweeps = (23, 10, 12), 5
+stencil = Jacobi3D(1.0, 0.25, backend='python', boundary_handling='clamp')
+grid = numpy.random.RandomState(2).random_sample(shape).astype(numpy.float32)
+slab = SlabDecomposition(shape, stencil.ghost_depth[0], world, rank)
+h = slab.h
+local = numpy.zeros(slab.local_shape, numpy.float32)
+lo, hi = max(0, slab.start - h), min(shape[0], slab.stop + h)
+local[lo - (slab.start - h):hi - (slab.start - h)] = grid[lo:hi]
+for _ in range(sweeps):
+    # a rank computes on [first real plane or its open-side ghosts .. ]: clamping at an open face
+    # only corrupts the outermost ghost plane, which is discarded
+    first = 0 if slab.open_lo else slab.first_real
+    last = local.shape[0] if slab.open_hi else slab.first_real + slab.planes
+    swept = reference_c(stencil, numpy.ascontiguousarray(local[first:last]))
+    new = numpy.zeros_like(local)
+    new[first:last] = swept
+    requests = []
+    for neighbour, source, destination in slab.sends():
+        requests.append(dist.isend(torch.from_numpy(numpy.ascontiguousarray(new[source[0]:source[1]])), neighbour))
+    for neighbour, source, destination in slab.sends():
+        # what I receive from `neighbour` lands where the neighbour's plan says; by symmetry that is
+        # my ghost range on that side
+        ghost = (0, h) if neighbour < rank else (h + slab.planes, 2 * h + slab.planes)
+        buffer = torch.empty((h,) + tuple(shape[1:]), dtype=torch.float32)
+        dist.recv(buffer, neighbour)
+        new[ghost[0]:ghost[1]] = buffer.numpy()
+    for request in requests:
+        request.wait()
+    local = new
+parts = [None] * world
+dist.all_gather_object(parts, numpy.array(local[slab.first_real:slab.first_real + slab.planes]))
+if rank == 0:
+    expected = grid
+    for _ in range(sweeps):
+        expected = reference_c(stencil, expected)
+    combined = numpy.concatenate(parts, axis=0)
+    assert (combined.view(numpy.uint32) == expected.view(numpy.uint32)).all(), "slab result differs"
+    print("SLAB_OK", world)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_logic_with_gloo(world, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    done = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+         "--master-addr", "127.0.0.1", "--master-port", str(29530 + world), str(script)],
+        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert done.returncode == 0, done.stdout[-2000:] + done.stderr[-3000:]
+    assert "SLAB_OK {}".format(world) in done.stdout
+
+
+@pytest.mark.gpu
+def test_slabs_on_two_gpus_match_single_gpu_and_oracle():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    done = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "multi_gpu_check.py")],
+        capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert done.returncode == 0 and "MULTI_GPU_CHECK PASSED" in done.stdout, \
+        done.stdout[-3000:] + done.stderr[-3000:]
