@@ -9,6 +9,15 @@ from .neighborhood import Neighborhood
 from .halo_enumerator import HaloEnumerator
 from .stencil_kernel import Stencil, SpecializedStencil, StencilArgConfig, product
 
+
+
+def pinned_empty(shape, dtype='float32', device_index=None):
+    """numpy array in page-locked host memory; pass such arrays to a ``backend='cuda'`` stencil to
+    make its host<->device copies asynchronous (additive helper, needs a GPU)."""
+    from .backend.cuda.runtime import pinned_empty as _pinned_empty
+    return _pinned_empty(shape, dtype, device_index)
+
+
 __all__ = ['Stencil', 'SpecializedStencil', 'StencilArgConfig', 'StencilException',
-           'Neighborhood', 'HaloEnumerator', 'product']
+           'Neighborhood', 'HaloEnumerator', 'product', 'pinned_empty']
 __version__ = '0.1.0'

@@ -163,3 +163,20 @@ def test_product_never_imports_the_oracle():
             "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.run([sys.executable, "-c", code], cwd=root, check=True)
+
+
+def test_pipelined_host_path_matches_oracle():
+    """Grids above the pipelining threshold are swept in axis-0 chunks on three streams."""
+    import stencil_code_b200
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    from stencil_code_b200.library.simple import SimpleKernel
+    from stencil_code_b200.backend.cuda.runtime import ConcreteCudaStencil
+    for make, shape in ((lambda backend, mode: LaplacianKernel(backend=backend, boundary_handling=mode), (96, 256, 512)),
+                        (lambda backend, mode: SimpleKernel(backend=backend, boundary_handling=mode), (4096, 4096))):
+        assert numpy.prod(shape) * 4 >= ConcreteCudaStencil.PIPELINE_MIN_BYTES
+        pinned = stencil_code_b200.pinned_empty(shape)
+        pinned[...] = (numpy.random.RandomState(13).random_sample(shape) * 1000).astype(numpy.float32)
+        for mode in ('clamp', 'copy'):
+            expected = oracle_output(make('python', mode), numpy.array(pinned), variant='c_parallel')
+            assert_bit_identical(numpy.array(make('cuda', mode)(pinned)), expected)
+            assert_bit_identical(numpy.array(make('cuda', mode)(numpy.array(pinned))), expected)   # pageable
