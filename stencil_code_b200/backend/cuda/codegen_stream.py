@@ -137,10 +137,49 @@ def applicable(program, domain, device_props):
     if any(s >= 2 ** 31 for s in program.shape):
         return False, "dimension above 2^31"
     try:
-        choose_config(program, domain, device_props)
+        if wants_plane_embedding(program, domain):
+            from .domain import Domain
+            lifted = embed_as_plane(program)
+            choose_config(lifted, Domain(lifted.shape, lifted.ghost_depth), device_props, {'embedded': True})
+        else:
+            choose_config(program, domain, device_props)
     except StencilException as error:
         return False, str(error)
     return True, "float32 rank-{} grid with 16-byte rows".format(program.dim)
+
+
+# ---- rank-2 stencils with a large window run as ONE plane of the rank-3 path (tiled, no streaming)
+def embed_as_plane(program):
+    """A view of a rank-2 program as rank 3 with a single plane: shape (1, n0, n1), taps (0, dy, dx).
+    Used when the row window is too large for registers (bilateral filter): such stencils are
+    compute bound, so a 2-d tile with a full halo and many resident CTAs beats row streaming."""
+    import copy as _copy
+
+    def lift(expr):
+        if isinstance(expr, pp.Tap):
+            return pp.Tap(expr.arg, (0,) + tuple(expr.offset), expr.ctype)
+        clone = _copy.copy(expr)
+        for name in ('left', 'right', 'operand', 'index'):
+            if hasattr(clone, name):
+                setattr(clone, name, lift(getattr(clone, name)))
+        if hasattr(clone, 'args') and isinstance(clone, pp.Call):
+            clone.args = [lift(a) for a in clone.args]
+        return clone
+
+    statements = []
+    for statement in program.statements:
+        clone = _copy.copy(statement)
+        clone.expr = lift(statement.expr)
+        statements.append(clone)
+    lifted = pp.PointProgram(3, (1,) + tuple(program.shape), program.out_ctype, program.args, statements,
+                             (0,) + tuple(program.ghost_depth), program.boundary)
+    return lifted
+
+
+def wants_plane_embedding(program, domain):
+    if program.dim != 2 or domain.is_slab:
+        return False
+    return Footprint(program, 1, program.boundary == 'copy').window_registers > 160
 
 
 # ---- footprint analysis -------------------------------------------------------------------------
@@ -195,7 +234,11 @@ def choose_config(program, domain, device_props, override=None):
         override[key.strip()] = value.strip() if key.strip() == 'mode' else int(value)
 
     candidates = []
-    if rank == 3:
+    embedded = bool(override.pop('embedded', False))
+    if embedded:
+        for TY, BY, NCW in ((16, 2, 8), (32, 4, 8), (32, 2, 16), (16, 4, 4), (8, 1, 8)):
+            candidates.append(dict(TX=128, TY=TY, BY=BY, NCW=NCW, U=1, prefetch=0))
+    elif rank == 3:
         for TY, BY, NCW, prefetch in ((64, 4, 16, 3), (32, 4, 8, 2), (32, 4, 8, 3), (16, 4, 4, 3),
                                       (32, 2, 16, 3), (16, 2, 8, 3), (8, 2, 4, 3), (8, 1, 8, 3)):
             candidates.append(dict(TX=128, TY=TY, BY=BY, NCW=NCW, U=1, prefetch=prefetch))
@@ -217,6 +260,8 @@ def choose_config(program, domain, device_props, override=None):
     for cand in candidates:
         fp = Footprint(program, cand['BY'], copy_center)
         mode = override.get('mode') or ('regwin' if fp.window_registers <= 160 else 'smem')
+        if embedded:
+            mode = 'smem'
         W = fp.window
         if mode == 'regwin':
             resident_units = fp.hz_hi - fp.release_age_regwin + 1
@@ -236,11 +281,21 @@ def choose_config(program, domain, device_props, override=None):
         stage_bytes = stage_floats * 4
         stage_bytes_aligned = (stage_bytes + 127) // 128 * 128
         smem = n_grids * S * stage_bytes_aligned + 3 * S * 8 + 128
+        static_smem = sum(a.size * 128 for a in table_plan(program, embedded)[3].values())
+        smem_total = smem + static_smem
         threads = (cand['NCW'] + 1) * 32
-        if smem > device_props.smem_per_block_optin:
+        if smem_total > device_props.smem_per_block_optin:
             continue
-        blocks_per_sm = min(device_props.smem_per_sm // (smem + 1024),
+        blocks_per_sm = min(device_props.smem_per_sm // (smem_total + 1024),
                             device_props.max_threads_per_sm // threads, 8)
+        if mode == 'smem':
+            # tap rows are re-read from smem per statement group: about one row of the footprint
+            # per register-block row stays live, plus accumulators and hoisted table entries
+            row_values = len({k[2] for k in fp.ages})
+            registers = 40 + cand['BY'] * (row_values + 4) + len(table_plan(program, embedded)[1])
+            blocks_per_sm = min(blocks_per_sm, max(1, device_props.regs_per_sm // (threads * registers)))
+        if 'blocks' in override:
+            blocks_per_sm = min(blocks_per_sm, override['blocks'])
         if blocks_per_sm < 1:
             continue
         # cost model: DRAM traffic per useful byte (halo rows, 32-byte sectors of the column pad,
@@ -265,12 +320,15 @@ def choose_config(program, domain, device_props, override=None):
         items = tiles * (-(-n_stream // chunk_len))
         fill = items / float(-(-items // slots) * slots)
         resident_warps = blocks_per_sm * cand['NCW']
-        score = waste * (1.0 + read_factor) / 2.0 / fill * (1.0 if resident_warps >= 12 else 1.1)
+        score = waste * (1.0 + read_factor) / 2.0 / (fill ** 0.5) * (1.0 if resident_warps >= 12 else 1.1)
         if 8.0 * program.npoints < 4e9:
             # measured on B200 (profiles/): sweeps of a few hundred microseconds are ramp/tail
             # dominated and run 3-6 % faster with more, smaller CTAs per SM than the traffic model says
             score *= {1: 1.10, 2: 1.04}.get(blocks_per_sm, 1.0)
+        if embedded:
+            score = float(len(candidates) - candidates.index(cand)) * -1.0      # first that fits wins
         config = StreamConfig(rank=rank, PADX=PADX, HX=hx, HY=hy, HZ_LO=fp.hz_lo, HZ_HI=fp.hz_hi, W=W,
+                              embedded=embedded,
                               mode=mode, S=S, PITCH=pitch, ROWS=rows, STAGE_FLOATS=stage_bytes_aligned // 4,
                               STAGE_BYTES=stage_bytes, smem_bytes=smem, threads=threads, NSUB=n_sub,
                               SUB_FLOATS=rows * pitch,
@@ -342,6 +400,7 @@ def _group_loads(cols):
 
 
 def generate(program, domain, cfg):
+    import os
     rank = cfg.rank
     fp = cfg.footprint
     grids = _grid_args(program)
@@ -367,17 +426,11 @@ def generate(program, domain, cfg):
     release_age = fp.release_age_regwin if regwin else HZ_LO
     rel_back = HZ_HI - release_age
 
-    # tables: constant-index entries are hoisted into registers, data-indexed small tables go to smem
-    data_tables, const_refs = set(), {}
-    for node in program.walk():
-        if isinstance(node, pp.TableRef):
-            constant = _const_index(node.index)
-            if constant is None:
-                data_tables.add(node.arg)
-            else:
-                const_refs[(node.arg, constant)] = node.ctype
-    smem_tables = {a.index: a for a in program.args if not a.used_as_grid
-                   and a.index in data_tables and a.size * a.dtype.itemsize <= 8192}
+    # tables: constant-index entries are hoisted into registers, data-indexed small tables go to
+    # smem -- bank-replicated (entry k of lane l at word k*32+l: conflict-free gathers) in the
+    # compute-bound tiled kernels
+    embedded = bool(getattr(cfg, 'embedded', False))
+    data_tables, const_refs, smem_tables, replicated = table_plan(program, embedded)
     guard_halo_body = (not clamp) and bool(data_tables)
 
     def tag(v):
@@ -397,10 +450,24 @@ def generate(program, domain, cfg):
             return value_name(g, slot_of(phase, age, (g, row, col)), row, col)
         return value_name(g, "a" + tag(age), row, col)
 
+    roll = find_rolled_run(program) if (not regwin and rank == 3) else None
+    if roll is not None and os.environ.get("STENCIL_CUDA_NO_ROLL"):
+        roll = None
+
     e = _Emitter()
     e.lines.append(PROLOGUE)
-    import os
     e.lines.append(PTX_HELPERS.replace("@STOP@", os.environ.get("STENCIL_CUDA_STORE_OP", ".cs")))
+    if roll is not None:
+        e("// per-tap parameters of the re-rolled neighbor loop ({} rows x {} taps)".format(
+            len(roll['dys']), len(roll['dxs'])))
+        for slot, param in enumerate(roll['params']):
+            if param is None:
+                continue
+            if param[0] == 'const':
+                values = ", ".join(pp.Const(v, param[1]).c_text() for v in param[2])
+                e("__constant__ {} cpar{}[{}] = {{{}}};".format(param[1], slot, len(param[2]), values))
+            else:
+                e("__constant__ int ipar{}[{}] = {{{}}};".format(slot, len(param[3]), ", ".join(map(str, param[3]))))
     e("// stream strategy: rank {} grid {} boundary {} | tile TX={} TY={} BY={} U={} ring S={} "
       "window W={} ({})".format(rank, shape, boundary, TX, TY, BY, U, S, W, cfg.mode))
     params = ["const {}* __restrict__ a{}".format(arg.ctype, arg.index) for arg in program.args]
@@ -418,14 +485,28 @@ def generate(program, domain, cfg):
     e("u64* const bar_land = bar_empty + {};".format(S))
     for index, arg in sorted(smem_tables.items()):
         e("__shared__ {} tab{}[{}];".format(arg.ctype, index, arg.size))
+    for index, arg in sorted(replicated.items()):
+        e("__shared__ float rep{}[{}];".format(index, arg.size * 32))
+    if roll is not None:
+        for slot, param in enumerate(roll['params']):
+            if param is not None and param[0] == 'table':
+                e("__shared__ {} spar{}[{}];".format(param[1], slot, len(param[3])))
     e("const int tid = threadIdx.x;")
     e("const int warp = tid >> 5;")
     e("const int lane = tid & 31;")
     e("const int x0 = blockIdx.x * {};".format(TX))
-    if rank == 3:
-        e("const int y0 = blockIdx.y * {};".format(TY))
-    e("const int u_begin = a0_begin + blockIdx.z * chunk_len;")
-    e("const int u_end = min(u_begin + chunk_len, a0_end);")
+    if embedded:
+        e("// one plane: a0_begin/a0_end select the ROWS this launch writes (tiles start at a0_begin)")
+        e("const int y0 = a0_begin + blockIdx.y * {};".format(TY))
+        e("const int row_end = a0_end;")
+        e("const int u_begin = 0;")
+        e("const int u_end = 1 + 0 * chunk_len;")
+    else:
+        if rank == 3:
+            e("const int y0 = blockIdx.y * {};".format(TY))
+            e("const int row_end = {};".format(N1))
+        e("const int u_begin = a0_begin + blockIdx.z * chunk_len;")
+        e("const int u_end = min(u_begin + chunk_len, a0_end);")
     e("if (u_begin >= u_end) return;")
     e("const int p_first = u_begin + ({});          // axis-0 index of streamed unit 0".format(HZ_LO))
     e("const int n_units = (u_end - u_begin) + {};".format(W - 1))
@@ -440,6 +521,14 @@ def generate(program, domain, cfg):
     e.close()
     for index, arg in sorted(smem_tables.items()):
         e("for (int k = tid; k < {n}; k += {t}) tab{i}[k] = a{i}[k];".format(n=arg.size, t=cfg.threads, i=index))
+    for index, arg in sorted(replicated.items()):
+        e("for (int k = tid; k < {n}; k += {t}) rep{i}[k] = a{i}[k >> 5];".format(
+            n=arg.size * 32, t=cfg.threads, i=index))
+    if roll is not None:
+        for slot, param in enumerate(roll['params']):
+            if param is not None and param[0] == 'table':
+                e("for (int k = tid; k < {n}; k += {t}) spar{s}[k] = a{a}[ipar{s}[k]];".format(
+                    n=len(param[3]), t=cfg.threads, s=slot, a=param[2]))
     e("__syncthreads();")
     e()
 
@@ -596,6 +685,87 @@ def generate(program, domain, cfg):
                 e(" ".join("{}{} = {}.{};".format(decl, name_of(phase, g, age, row, c), tmp, "xyzw"[c - first])
                            for c in used))
 
+    current_tap_text, current_acc = [None], [None]
+
+    def emit_rolled(phase, loaded, acc):
+        """the re-rolled neighbor loop: runtime loop over tap rows, taps of a row unrolled"""
+        import copy as _copy
+        template = roll['template']
+        taps, pures = [], []
+        _shape_of(template.expr, taps, pures)
+        moving_ids = {id(taps[k]) for k in roll['moving']}
+        slot_counter = [0]
+
+        def substitute(expr):
+            if isinstance(expr, pp.Tap):
+                return expr
+            if _is_pure(expr):
+                slot = slot_counter[0]
+                slot_counter[0] += 1
+                if roll['params'][slot] is None:
+                    return expr
+                return pp.LocalRef("@P{}@".format(slot), expr.ctype)
+            clone = _copy.copy(expr)
+            for name in ('left', 'right', 'operand', 'index'):
+                if hasattr(clone, name):
+                    setattr(clone, name, substitute(getattr(clone, name)))
+            if isinstance(clone, pp.Call):
+                clone.args = [substitute(a) for a in clone.args]
+            return clone
+        # children() order must match _shape_of: Bin(left,right), Neg/Cast(operand), Call(args), TableRef(index)
+        body = pp.Store(template.op, substitute(template.expr))
+        dz, dys, dxs, gi = roll['dz'], roll['dys'], roll['dxs'], roll['grid']
+        n_dx = len(dxs)
+        # taps that do not move with the neighbor (e.g. the centre value) are loaded once
+        wanted = {}
+        for tap in taps:
+            if id(tap) not in moving_ids:
+                tz, ty, tx = _tap3(tap.offset)
+                wanted.setdefault((tap.arg, tz), set()).update({b + ty for b in range(BY)})
+        for (ga, age), rows in sorted(wanted.items()):
+            keys = [k for k, ages in fp.ages.items()
+                    if k[0] == ga and age in ages and k[1] in rows and (ga, age, k[1], k[2]) not in loaded]
+            if keys:
+                emit_loads(phase, ga, age, keys)
+                loaded.update((ga, age, k[1], k[2]) for k in keys)
+        e("#pragma unroll 1")
+        e.open("for (int tr_ = 0; tr_ < {}; ++tr_)".format(len(dys)))
+        e("const float* const rp = u{}_{} + ({} + tr_) * {};".format(gi, tag(dz), dys[0], PITCH))
+        e("const int pk = tr_ * {};".format(n_dx))
+        cols = sorted({j + dx for j in range(4) for dx in dxs})
+        for b in range(BY):
+            for first, width, used in _group_loads(set(cols)):
+                offset = b * PITCH + first
+                if width == 1:
+                    e("const float rw{}_{} = rp[{}];".format(b, tag(used[0]), offset))
+                    continue
+                counter[0] += 1
+                tmp = "q{}".format(counter[0])
+                vec = "float4" if width == 4 else "float2"
+                e("const {v} {t} = *reinterpret_cast<const {v}*>(rp + ({o}));".format(v=vec, t=tmp, o=offset))
+                e(" ".join("const float rw{}_{} = {}.{};".format(b, tag(c), tmp, "xyzw"[c - first]) for c in used))
+        for c_index, dx in enumerate(dxs):
+            for b in range(BY):
+                for j in range(4):
+                    def tap_text(tap, b=b, j=j, dx=dx):
+                        if id(tap) in moving_ids:
+                            return "rw{}_{}".format(b, tag(j + dx))
+                        tz, ty, tx = _tap3(tap.offset)
+                        return name_of(phase, tap.arg, tz, b + ty, j + tx)
+                    single = pp.PointProgram(program.dim, program.shape, program.out_ctype, program.args,
+                                             [body], program.ghost_depth, program.boundary)
+                    current_tap_text[0], current_acc[0] = tap_text, acc[b][j]
+                    text = emit_statements(single, tap_text, table_text, acc=acc[b][j], indent="")[0]
+                    text = _LOCAL_NAME.sub(lambda m: "{}_{}_{}".format(m.group(0), b, j), text)
+                    for slot, param in enumerate(roll['params']):
+                        if param is not None:
+                            array = "cpar" if param[0] == 'const' else "spar"
+                            text = text.replace("@P{}@".format(slot), "{}{}[pk + {}]".format(array, slot, c_index))
+                    if guard_halo_body:
+                        text = "if (!(halo_mask & {}u)) {{ {} }}".format(1 << (b * 4 + j), text)
+                    e(text)
+        e.close()
+
     def emit_release():
         e("__syncwarp();")
         if U == 1:
@@ -611,6 +781,16 @@ def generate(program, domain, cfg):
         constant = _const_index(ref.index)
         if constant is not None:
             return "tc{}_{}".format(ref.arg, constant)
+        fast = _fast_floor_index(ref.index)
+        if fast is not None and (ref.arg in replicated or ref.arg in smem_tables):
+            # the enclosing emitter prints the float operand; see _fast_floor_index
+            operand = pp.expr_to_c(fast, current_tap_text[0], table_text, out_text=current_acc[0])
+            bits = "(__float_as_int(__fadd_rz(fabsf({}), 8388608.0f)) - 0x4B000000)".format(operand)
+            if ref.arg in replicated:
+                return "rep{}[({} << 5) + lane]".format(ref.arg, bits)
+            return "tab{}[{}]".format(ref.arg, bits)
+        if ref.arg in replicated:
+            return "rep{}[(({}) << 5) + lane]".format(ref.arg, index_text)
         if ref.arg in smem_tables:
             return "tab{}[{}]".format(ref.arg, index_text)
         return "a{}[{}]".format(ref.arg, index_text)
@@ -670,7 +850,11 @@ def generate(program, domain, cfg):
                 ztests.append("z >= {}".format(i_hi[0]))
             e("const bool z_halo = {};".format(" || ".join(ztests) if ztests else "false"))
             e.open("if (!z_halo)")
-        for statement in program.statements:
+        for s_index, statement in enumerate(program.statements):
+            if roll is not None and roll['start'] <= s_index < roll['stop']:
+                if s_index == roll['start']:
+                    emit_rolled(phase, loaded, acc)
+                continue
             if not regwin:
                 wanted = {}
                 stack = [statement.expr]
@@ -694,6 +878,7 @@ def generate(program, domain, cfg):
                         return name_of(phase, tap.arg, dz, b + dy, j + dx)
                     single = pp.PointProgram(program.dim, program.shape, program.out_ctype, program.args,
                                              [statement], program.ghost_depth, program.boundary)
+                    current_tap_text[0], current_acc[0] = tap_text, acc[b][j]
                     text = emit_statements(single, tap_text, table_text, acc=acc[b][j], indent="")[0]
                     text = _LOCAL_NAME.sub(lambda m: "{}_{}_{}".format(m.group(0), b, j), text)
                     if guard_halo_body:
@@ -710,7 +895,7 @@ def generate(program, domain, cfg):
                     e("if (z_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), acc[b][j], value))
         for b in range(BY):
             if rank == 3:
-                cond = "col_ok && gy + {} < {}".format(b, N1)
+                cond = "col_ok && gy + {} < row_end".format(b)
                 address = "out + ((i64)z * {} + (gy + {})) * {} + gx".format(N1, b, N2)
             else:
                 cond = "col_ok"
@@ -730,6 +915,144 @@ def generate(program, domain, cfg):
     return e.text()
 
 
+def _fast_floor_index(index):
+    """``abs((int)x)`` with x float32 -> x, else None.  For |x| < 2^23 (any valid table index is)
+    the value equals floor(|x|), which one round-toward-zero add of 2^23 leaves in the mantissa:
+    a full-rate FADD.RZ instead of a quarter-rate F2I plus IABS."""
+    if isinstance(index, pp.Call) and index.func == 'abs':
+        inner = index.args[0]
+        if isinstance(inner, pp.Cast) and inner.ctype == pp.INT and inner.operand.ctype == pp.FLOAT:
+            return inner.operand
+    return None
+
+
+def table_plan(program, replicate):
+    """(constant-index refs hoisted to registers, tables staged in smem, tables bank-replicated)"""
+    data_tables, const_refs = set(), {}
+    for node in program.walk():
+        if isinstance(node, pp.TableRef):
+            constant = _const_index(node.index)
+            if constant is None:
+                data_tables.add(node.arg)
+            else:
+                const_refs[(node.arg, constant)] = node.ctype
+    candidates = [a for a in program.args if not a.used_as_grid and a.index in data_tables]
+    replicated = {a.index: a for a in candidates
+                  if replicate and a.ctype == pp.FLOAT and a.size <= 256}
+    smem_tables = {a.index: a for a in candidates
+                   if a.index not in replicated and a.size * a.dtype.itemsize <= 8192}
+    return data_tables, const_refs, smem_tables, replicated
+
+
+# ---- re-rolling of large neighborhoods -------------------------------------------------------------
+class _Pure(object):
+    """placeholder for a tap-dependent but data-independent sub-expression (a folded distance(),
+    a table entry at a folded index): becomes one entry per tap of a parameter table"""
+    def __init__(self, slot, ctype):
+        self.slot, self.ctype = slot, ctype
+
+
+def _is_pure(expr):
+    if isinstance(expr, (pp.Tap, pp.OutRef, pp.LocalRef)):
+        return False
+    if isinstance(expr, pp.TableRef) and _const_index(expr.index) is None:
+        return False
+    return all(_is_pure(c) for c in expr.children())
+
+
+def _shape_of(expr, taps, pures):
+    """structural key of an expression with taps and maximal pure sub-expressions abstracted"""
+    if isinstance(expr, pp.Tap):
+        taps.append(expr)
+        return ('tap', expr.arg, expr.ctype)
+    if _is_pure(expr):
+        pures.append(expr)
+        return ('pure', expr.ctype)
+    if isinstance(expr, pp.OutRef):
+        return ('out',)
+    if isinstance(expr, pp.LocalRef):
+        return ('local', expr.name)
+    head = (type(expr).__name__, getattr(expr, 'op', None), getattr(expr, 'func', None), expr.ctype,
+            getattr(expr, 'arg', None))
+    return head + tuple(_shape_of(c, taps, pures) for c in expr.children())
+
+
+def _pure_value(expr):
+    """('const', value) or ('table', arg, index) for the supported pure forms, else None"""
+    if isinstance(expr, pp.Const):
+        return ('const', expr.value)
+    if isinstance(expr, pp.TableRef):
+        return ('table', expr.arg, _const_index(expr.index))
+    return None
+
+
+def find_rolled_run(program, min_taps=48):
+    """Longest run of consecutive stores that are one statement template applied over a full
+    (dy, dx) rectangle of tap offsets in row-major order.  Returns None if there is none worth
+    rolling.  Rolling keeps the statement order, hence the bits of the result."""
+    statements = program.statements
+    infos = []
+    for statement in statements:
+        if not isinstance(statement, pp.Store):
+            infos.append(None)
+            continue
+        taps, pures = [], []
+        key = (statement.op, _shape_of(statement.expr, taps, pures))
+        values = [_pure_value(q) for q in pures]
+        infos.append(None if any(v is None for v in values) else (key, taps, pures, values))
+    best = None
+    start = 0
+    while start < len(statements):
+        if infos[start] is None:
+            start += 1
+            continue
+        stop = start
+        while stop < len(statements) and infos[stop] is not None and infos[stop][0] == infos[start][0]:
+            stop += 1
+        if stop - start >= min_taps and (best is None or stop - start > best[1] - best[0]):
+            best = (start, stop)
+        start = stop
+    if best is None:
+        return None
+    start, stop = best
+    run = infos[start:stop]
+    n_taps = len(run[0][1])
+    moving = [k for k in range(n_taps) if len({info[1][k].offset for info in run}) > 1]
+    if not moving:
+        return None
+    offsets = []
+    for info in run:
+        these = {info[1][k].offset for k in moving}
+        if len(these) != 1:
+            return None                                   # several different moving offsets in one statement
+        offsets.append(_tap3(next(iter(these))))
+    if len({o[0] for o in offsets}) != 1 or len({info[1][moving[0]].arg for info in run}) != 1:
+        return None
+    dys = sorted({o[1] for o in offsets})
+    dxs = sorted({o[2] for o in offsets})
+    expected = [(offsets[0][0], dy, dx) for dy in dys for dx in dxs]
+    if offsets != expected or dys != list(range(dys[0], dys[-1] + 1)) or dxs != list(range(dxs[0], dxs[-1] + 1)):
+        return None
+    if len(dys) < 3:
+        return None
+    params = []
+    for slot in range(len(run[0][2])):
+        values = [info[3][slot] for info in run]
+        kinds = {v[0] for v in values}
+        if len(kinds) != 1:
+            return None
+        if len(set(values)) == 1:
+            params.append(None)                           # same for every tap: stays inline
+        elif kinds == {'const'}:
+            params.append(('const', run[0][2][slot].ctype, [v[1] for v in values]))
+        else:
+            if len({v[1] for v in values}) != 1:
+                return None
+            params.append(('table', run[0][2][slot].ctype, values[0][1], [v[2] for v in values]))
+    return dict(start=start, stop=stop, dz=offsets[0][0], dys=dys, dxs=dxs, moving=set(moving),
+                params=params, template=statements[start], grid=run[0][1][moving[0]].arg)
+
+
 def _const_index(index):
     if isinstance(index, pp.Const):
         return int(index.value)
@@ -741,8 +1064,17 @@ def _const_index(index):
 def make_plan(program, domain, device_props, options, override=None):
     from .transformer import CudaPlan
     from .planner import Launch
-    cfg = choose_config(program, domain, device_props, override)
-    source = generate(program, domain, cfg)
+    from .domain import Domain
+    original = program
+    embedded = wants_plane_embedding(program, domain)
+    if embedded:
+        program = embed_as_plane(program)
+        domain3 = Domain(program.shape, program.ghost_depth)
+        cfg = choose_config(program, domain3, device_props, dict(override or {}, embedded=True))
+        source = generate(program, domain3, cfg)
+    else:
+        cfg = choose_config(program, domain, device_props, override)
+        source = generate(program, domain, cfg)
     rank = cfg.rank
     shape = program.shape
     specs = []
@@ -758,21 +1090,24 @@ def make_plan(program, domain, device_props, options, override=None):
     tiles_y = -(-shape[1] // cfg.TY) if rank == 3 else 1
     slots = device_props.sm_count * cfg.blocks_per_sm
     min_chunk = max(4 * cfg.W, 16) if rank == 3 else max(4 * cfg.U, 64)
+    static_smem = sum(a.size * 128 for a in table_plan(program, embedded)[3].values())
 
     def geometry(a0_begin, a0_end):
+        if embedded:
+            rows = a0_end - a0_begin
+            launch = Launch((tiles_x, -(-rows // cfg.TY), 1), (cfg.threads, 1, 1), cfg.smem_bytes)
+            launch.extra = (1,)
+            return launch
         n_units = a0_end - a0_begin
         chunks = plan_chunks(n_units, tiles_x * tiles_y, slots, cfg.W, min_chunk)
         chunk_len = -(-n_units // chunks)
         if rank == 2:
             chunk_len = -(-chunk_len // cfg.U) * cfg.U if chunk_len > cfg.U else chunk_len
         chunks = -(-n_units // chunk_len)
-        import os
-        cluster = int(os.environ.get("STENCIL_CUDA_CLUSTER", "1"))
-        if tiles_x % cluster:
-            cluster = 1
-        launch = Launch((tiles_x, tiles_y, chunks), (cfg.threads, 1, 1), cfg.smem_bytes, (cluster, 1, 1))
+        launch = Launch((tiles_x, tiles_y, chunks), (cfg.threads, 1, 1), cfg.smem_bytes)
         launch.extra = (chunk_len,)
         return launch
 
-    return CudaPlan(program, domain, 'stream', source, FUNCTION, options, geometry,
-                    tensor_maps=specs, notes={'config': cfg.describe()})
+    notes = dict(cfg.describe(), embedded_plane=embedded, static_smem=static_smem)
+    return CudaPlan(original, domain, 'stream', source, FUNCTION, options, geometry,
+                    tensor_maps=specs, notes={'config': notes})

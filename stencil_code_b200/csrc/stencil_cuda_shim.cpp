@@ -423,7 +423,8 @@ int sc_function_info(sc_module* module, const char* function, int* regs, int* st
 }
 
 static int optin_smem(sc_module* module, const char* function, CUfunction fn, size_t dynamic_smem) {
-    if (dynamic_smem <= 48 * 1024) return SC_OK;
+    // static + dynamic above 48 KB needs the opt-in too, so any non-trivial dynamic size is declared
+    if (dynamic_smem <= 8 * 1024) return SC_OK;
     auto key = std::make_pair(current_device_index(), std::string(function));
     {
         std::lock_guard<std::mutex> lock(g_mutex);

@@ -107,6 +107,8 @@ CASES = [
          shape=(10, 8, 12), scale=1, golden=False),
     Case("odd_weights", _plain(OddWeights), shape=(14, 12), golden=False),
     Case("cross3d_r2", _plain(Radius2Cross3D), extra=(WEIGHTS3,), shape=(9, 10, 12), golden=False),
+    Case("bilateral_r9", lambda b, backend: BetterBilateralFilter(sigma_d=3, sigma_i=70, backend=backend),
+         shape=(40, 128), scale=255, modes=('clamp',), golden=False),
     Case("convolution5_modes",
          lambda b, backend: ConvolutionFilter(convolution_array=CONV5_BENCH, backend=backend, boundary_handling=b),
          shape=(20, 24), golden=False),

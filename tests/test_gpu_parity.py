@@ -82,6 +82,7 @@ SHAPE_SWEEP = {
     "odd_weights": [(64, 128), (33, 36)],
     "stencil1d": [(8,), (1000,), (4096,)],
     "better_bilateral": [(64, 32), (40, 128)],
+    "bilateral_r9": [(70, 260), (33, 1028)],
 }
 SWEEP = [(case, mode, shape) for case in CASES if case.name in SHAPE_SWEEP
          for mode in case.modes for shape in SHAPE_SWEEP[case.name]]
