@@ -17,10 +17,12 @@ barrier, taps from local memory) and its per-dimension halo-copy kernels
     phase so that rotation is pure renaming).  Stencils whose window would not fit in registers
     (bilateral filter, radius 9) read every tap row from the shared-memory ring instead.
   * All four boundary modes live in the same kernel.  Along axis 0 the producer clamps the TMA
-    coordinate; inside the plane the producer warp overwrites the zero-filled out-of-grid halo
-    cells of boundary tiles with the clamped values before releasing the stage ('clamp');
-    'zero'/'copy' select 0 / the centre value for halo points at the store.  Every output point
-    of the launch is written exactly once, with 128-bit stores.
+    coordinate (rank 3) / the consumer clamps the row index (rank 2).  Inside the plane 'clamp'
+    is applied while the consumers load their registers: halo rows are read through clamped row
+    offsets and out-of-grid columns (zero-filled by TMA) are overwritten by a select cascade that
+    only the warps of edge tiles execute.  'zero'/'copy' select 0 / the centre value for halo
+    points at the store.  Every output point of the launch is written exactly once, with 128-bit
+    stores.
   * Arithmetic is the typed per-point program, statement for statement, with FMA contraction
     off -- bit-identical to the direct strategy and to the reference's C.
 
@@ -112,7 +114,7 @@ def _grid_args(program):
     return [a for a in program.args if a.used_as_grid]
 
 
-def applicable(program, domain, device_props):
+def applicable(program, domain, device_props, forced=False):
     if program.dim not in (2, 3):
         return False, "rank {} (stream handles 2 and 3)".format(program.dim)
     if program.out_ctype != pp.FLOAT:
@@ -131,6 +133,10 @@ def applicable(program, domain, device_props):
         return False, "a single plane/row along the streaming axis"
     if program.npoints < 4096:
         return False, "tiny grid"
+    if program.npoints < (1 << 21) and not forced:
+        # measured on B200: a 1024^2 sweep takes 6 us with one thread per point and 12 us through
+        # the TMA pipeline (fill latency of a handful of CTAs); the grid is L2 resident either way
+        return False, "small grid ({} points): launch-latency bound, direct is faster".format(program.npoints)
     lo, hi = program.tap_extent()
     if max(-lo[-1], hi[-1]) > 12:
         return False, "tap radius along the fast axis above 12"
@@ -208,6 +214,13 @@ class Footprint(object):
             for b in range(BY):
                 for j in range(4):
                     self.ages.setdefault((0, b, j), set()).add(0)
+        if program.boundary == 'clamp':
+            # a column left of the grid takes the value of its right-hand neighbour (and vice versa
+            # on the right), cascading up to the thread's own columns: those must be loaded too
+            for (g, row, col), ages in list(self.ages.items()):
+                inner = range(col + 1, 1) if col < 0 else range(3, col) if col > 3 else ()
+                for c in inner:
+                    self.ages.setdefault((g, row, c), set()).update(ages)
         all_ages = [a for s in self.ages.values() for a in s] or [0]
         self.hz_lo, self.hz_hi = min(min(all_ages), 0), max(max(all_ages), 0)
         self.window = self.hz_hi - self.hz_lo + 1
@@ -422,7 +435,6 @@ def generate(program, domain, cfg):
     c_lo, c_hi = domain.clamp_lo, domain.clamp_hi
     i_lo, i_hi = domain.interior_lo, domain.interior_hi
     col_axis = rank - 1
-    needs_patch = clamp and (HX > 0 or HY > 0)
     release_age = fp.release_age_regwin if regwin else HZ_LO
     rel_back = HZ_HI - release_age
 
@@ -482,7 +494,6 @@ def generate(program, domain, cfg):
     e("float* const ring = reinterpret_cast<float*>(smem_raw);")
     e("u64* const bar_full = reinterpret_cast<u64*>(smem_raw + {});".format(cfg.n_grids * S * SF * 4))
     e("u64* const bar_empty = bar_full + {};".format(S))
-    e("u64* const bar_land = bar_empty + {};".format(S))
     for index, arg in sorted(smem_tables.items()):
         e("__shared__ {} tab{}[{}];".format(arg.ctype, index, arg.size))
     for index, arg in sorted(replicated.items()):
@@ -515,7 +526,6 @@ def generate(program, domain, cfg):
     e.open("for (int s = 0; s < {}; ++s)".format(S))
     e("mbar_init(&bar_full[s], 1);")
     e("mbar_init(&bar_empty[s], {});".format(NCW))
-    e("mbar_init(&bar_land[s], 1);")
     e.close()
     e("fence_barrier_init();")
     e.close()
@@ -536,24 +546,11 @@ def generate(program, domain, cfg):
     e.open("if (warp == {})".format(NCW))
     for arg in grids:
         e("if (lane == 0) tma_prefetch_desc(&tm{});".format(arg.index))
-    if needs_patch:
-        edges = []
-        if HX:
-            edges += ["x0 == 0", "x0 + {} > {}".format(TX + HX, N2)]
-        if rank == 3 and HY:
-            edges += ["y0 == 0", "y0 + {} > {}".format(TY + HY, N1)]
-        e("const bool patch = {};   // tile touches a clamped face".format(" || ".join(edges)))
-        lag = max(1, S - ((rel_back // U) + 1 + (1 if U > 1 else 0)))
-        e("const int lag = patch ? {} : 0;".format(lag))
-    else:
-        e("const bool patch = false;")
-        e("const int lag = 0;")
-    e.open("for (int k = 0; k < n_stages + lag; ++k)")
-    e.open("if (k < n_stages)")
+    e.open("for (int k = 0; k < n_stages; ++k)")
     e("const int s = k % {};".format(S))
     e("if (k >= {S}) mbar_wait(&bar_empty[s], ((k / {S}) - 1) & 1);".format(S=S))
     e.open("if (lane == 0)")
-    e("u64* const bar = patch ? &bar_land[s] : &bar_full[s];")
+    e("u64* const bar = &bar_full[s];")
     e("mbar_expect_tx(bar, {});".format(cfg.STAGE_BYTES * cfg.n_grids))
     if rank == 2:
         e("const int r0 = p_first + k * {};   // rows outside the grid are zero-filled and never read".format(U))
@@ -569,57 +566,6 @@ def generate(program, domain, cfg):
             e("tma_load_2d(dst, &tm{g}, bar, xs, r0);".format(g=arg.index))
             e.close()
     e.close()
-    e.close()
-    if needs_patch:
-        e.open("if (patch && k >= lag)")
-        e("const int j = k - lag;")
-        e("const int s = j % {};".format(S))
-        e("mbar_wait(&bar_land[s], (j / {}) & 1);".format(S))
-        for arg in grids:
-            e("float* const st{g} = ring + ({k} + s) * {sf};".format(g=arg.index, k=ring_of[arg.index] * S, sf=SF))
-        # columns first, then whole rows (3-d): corner cells end up clamped in both directions
-        if HX:
-            e.open("for (int w = 0; w < {}; ++w)".format(NSUB))
-            e("const int xs = x0 + w * 128;          // first grid column of this sub-tile")
-            e("if (xs >= {}) break;".format(N2))
-            e("const int col_first = {};".format(PADX))
-            e("const int col_last = {} + min({}, {} - 1 - xs);".format(PADX, 128 + HX - 1, N2))
-            e.open("for (int r = lane; r < {}; r += 32)".format(ROWS))
-            for arg in grids:
-                base = "st{}[w * {} + r * {} + ".format(arg.index, SUBF, PITCH)
-                e.open("if (xs == 0)")
-                e("const float edge = {}col_first];".format(base))
-                for c in range(1, HX + 1):
-                    e("{}col_first - {}] = edge;".format(base, c))
-                e.close()
-                e.open("if (xs + {} > {})".format(128 + HX, N2))
-                e("const float edge = {}col_last];".format(base))
-                for c in range(1, HX + 1):
-                    e("if (col_last + {c} < {p}) {b}col_last + {c}] = edge;".format(c=c, p=PITCH, b=base))
-                e.close()
-            e.close()
-            e.close()
-            e("__syncwarp();")
-        if rank == 3 and HY:
-            e("const int row_last = {} + min({}, {} - 1 - y0);".format(HY, TY + HY - 1, N1))
-            e.open("for (int c = lane; c < {}; c += 32)".format(PITCH))
-            for arg in grids:
-                e.open("if (y0 == 0)")
-                e("const float edge = st{}[{} + c];".format(arg.index, HY * PITCH))
-                for r in range(1, HY + 1):
-                    e("st{}[{} + c] = edge;".format(arg.index, (HY - r) * PITCH))
-                e.close()
-                e.open("if (y0 + {} > {})".format(TY + HY, N1))
-                e("const float edge = st{}[row_last * {} + c];".format(arg.index, PITCH))
-                for r in range(1, HY + 1):
-                    e("if (row_last + {r} < {rows}) st{g}[(row_last + {r}) * {p} + c] = edge;".format(
-                        r=r, rows=ROWS, g=arg.index, p=PITCH))
-                e.close()
-            e.close()
-        e("fence_proxy_async();")
-        e("__syncwarp();")
-        e("if (lane == 0) mbar_arrive(&bar_full[s]);")
-        e.close()
     e.close()   # for k
     e("return;")
     e.close()   # producer
@@ -636,6 +582,19 @@ def generate(program, domain, cfg):
         e("const int sbase = warp * {} + {} + lane * 4;   // own 128-column sub-tile".format(SUBF, PADX))
     e("const int gx = x0 + tq * 4;          // first of this thread's 4 columns")
     e("const bool col_ok = gx < {};".format(N2))
+    clamp_rows = clamp and rank == 3 and (HY > 0 or BY > 1)
+    clamp_cols = clamp and HX > 0
+    if clamp_rows:
+        e("// 'clamp' inside the plane is applied while loading: rows through clamped row offsets,")
+        e("// columns by a select cascade that only warps of edge tiles execute")
+        for row in sorted({k[1] for k in fp.ages}):
+            e("const int ro{t} = (min(max(gy + ({r}), 0), {n}) - (gy + ({r}))) * {p};".format(
+                t=tag(row), r=row, n=N1 - 1, p=PITCH))
+    if clamp_cols:
+        if rank == 3:
+            e("const bool x_edge = x0 == 0 || x0 + {} > {};".format(TX + HX, N2))
+        else:
+            e("const bool x_edge = x0 + warp * 128 == 0 || x0 + warp * 128 + {} > {};".format(128 + HX, N2))
     if not clamp:
         e("u32 halo_mask = 0;                   // bit (b*4+j): the point lies in the in-plane halo")
         for b in range(BY):
@@ -665,16 +624,27 @@ def generate(program, domain, cfg):
 
     counter = [0]
 
+    def emit_column_fix(names_by_col):
+        """cascade the nearest in-grid column outward (names_by_col: col -> register name)"""
+        left = sorted((c for c in names_by_col if c < 0), reverse=True)
+        right = sorted(c for c in names_by_col if c > 3)
+        for c in left:
+            e("if (gx + ({}) < 0) {} = {};".format(c, names_by_col[c], names_by_col[c + 1]))
+        for c in right:
+            e("if (gx + {} > {}) {} = {};".format(c, N2 - 1, names_by_col[c], names_by_col[c - 1]))
+
     def emit_loads(phase, g, age, keys):
         """shared memory -> registers for the (row, col) values `keys` of grid g at `age`"""
         pointer = "u{}_{}".format(g, tag(age))
-        decl = "" if regwin else "const float "
+        decl = "" if regwin else ("float " if clamp_cols else "const float ")
         by_row = {}
         for (_, row, col) in keys:
             by_row.setdefault(row, set()).add(col)
         for row in sorted(by_row):
             for first, width, used in _group_loads(by_row[row]):
-                offset = row * PITCH + first
+                offset = "{}".format(row * PITCH + first)
+                if clamp_rows:
+                    offset = "ro{} + ({})".format(tag(row), offset)
                 if width == 1:
                     e("{}{} = {}[{}];".format(decl, name_of(phase, g, age, row, used[0]), pointer, offset))
                     continue
@@ -684,6 +654,19 @@ def generate(program, domain, cfg):
                 e("const {v} {t} = *reinterpret_cast<const {v}*>({p} + ({o}));".format(v=vec, t=tmp, p=pointer, o=offset))
                 e(" ".join("{}{} = {}.{};".format(decl, name_of(phase, g, age, row, c), tmp, "xyzw"[c - first])
                            for c in used))
+        n_outer = sum(1 for cols in by_row.values() for c in cols if c < 0 or c > 3)
+        if clamp_cols and n_outer:
+            # few selects: leave them unconditional (loop-invariant predicates, no basic-block split
+            # between the loads and the arithmetic); many: only edge-tile warps execute them
+            branch = n_outer > int(os.environ.get("STENCIL_CUDA_FIX_BRANCH", "8"))
+            e.open("if (x_edge)" if branch else "")
+            for row in sorted(by_row):
+                outer = [c for c in by_row[row] if c < 0 or c > 3]
+                if not outer:
+                    continue
+                span = range(min(min(outer), 0), max(max(outer), 3) + 1)
+                emit_column_fix({c: name_of(phase, g, age, row, c) for c in span if (g, row, c) in fp.ages})
+            e.close()
 
     current_tap_text, current_acc = [None], [None]
 
@@ -730,20 +713,32 @@ def generate(program, domain, cfg):
                 loaded.update((ga, age, k[1], k[2]) for k in keys)
         e("#pragma unroll 1")
         e.open("for (int tr_ = 0; tr_ < {}; ++tr_)".format(len(dys)))
-        e("const float* const rp = u{}_{} + ({} + tr_) * {};".format(gi, tag(dz), dys[0], PITCH))
         e("const int pk = tr_ * {};".format(n_dx))
         cols = sorted({j + dx for j in range(4) for dx in dxs})
+        if clamp_cols:
+            cols = list(range(min(cols[0], 0), max(cols[-1], 3) + 1))
+        decl = "float" if clamp_cols else "const float"
         for b in range(BY):
+            if clamp_rows:
+                e("const float* const rp{b} = u{g}_{z} + (min(max(gy + ({r}) + tr_, 0), {n}) - gy) * {p};".format(
+                    b=b, g=gi, z=tag(dz), r=b + dys[0], n=N1 - 1, p=PITCH))
+            else:
+                e("const float* const rp{b} = u{g}_{z} + ({r} + tr_) * {p};".format(
+                    b=b, g=gi, z=tag(dz), r=b + dys[0], p=PITCH))
             for first, width, used in _group_loads(set(cols)):
-                offset = b * PITCH + first
                 if width == 1:
-                    e("const float rw{}_{} = rp[{}];".format(b, tag(used[0]), offset))
+                    e("{} rw{}_{} = rp{}[{}];".format(decl, b, tag(used[0]), b, first))
                     continue
                 counter[0] += 1
                 tmp = "q{}".format(counter[0])
                 vec = "float4" if width == 4 else "float2"
-                e("const {v} {t} = *reinterpret_cast<const {v}*>(rp + ({o}));".format(v=vec, t=tmp, o=offset))
-                e(" ".join("const float rw{}_{} = {}.{};".format(b, tag(c), tmp, "xyzw"[c - first]) for c in used))
+                e("const {v} {t} = *reinterpret_cast<const {v}*>(rp{b} + ({o}));".format(v=vec, t=tmp, b=b, o=first))
+                e(" ".join("{} rw{}_{} = {}.{};".format(decl, b, tag(c), tmp, "xyzw"[c - first]) for c in used))
+        if clamp_cols:
+            e.open("if (x_edge)")
+            for b in range(BY):
+                emit_column_fix({c: "rw{}_{}".format(b, tag(c)) for c in cols})
+            e.close()
         for c_index, dx in enumerate(dxs):
             for b in range(BY):
                 for j in range(4):
@@ -849,7 +844,11 @@ def generate(program, domain, cfg):
             if i_hi[0] < N0:
                 ztests.append("z >= {}".format(i_hi[0]))
             e("const bool z_halo = {};".format(" || ".join(ztests) if ztests else "false"))
-            e.open("if (!z_halo)")
+            # halo planes/rows are computed like any other and overwritten below: keeping the
+            # arithmetic in the same basic block as the window loads lets ptxas overlap them.  Only
+            # data-indexed tables (garbage index from zero-filled cells) force a real branch.
+            if guard_halo_body:
+                e.open("if (!z_halo)")
         for s_index, statement in enumerate(program.statements):
             if roll is not None and roll['start'] <= s_index < roll['stop']:
                 if s_index == roll['start']:
@@ -888,11 +887,14 @@ def generate(program, domain, cfg):
                         text = "if (!(halo_mask & {}u)) {{ {} }}".format(1 << (b * 4 + j), text)
                     e(text)
         if not clamp:
-            e.close()   # if (!z_halo)
+            if guard_halo_body:
+                e.close()   # if (!z_halo)
+            e.open("if (z_halo || halo_mask)")        # rare: one uniform branch for interior threads
             for b in range(BY):
                 for j in range(4):
                     value = name_of(phase, 0, 0, b, j) if copy else "0.0f"
                     e("if (z_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), acc[b][j], value))
+            e.close()
         for b in range(BY):
             if rank == 3:
                 cond = "col_ok && gy + {} < row_end".format(b)

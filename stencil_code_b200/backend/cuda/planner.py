@@ -47,7 +47,7 @@ def plan(program, domain, device_props=None, forced_strategy=None, options=()):
         strategy = 'stream' if ok else 'direct'
     if strategy == 'stream':
         from . import codegen_stream
-        ok, why = codegen_stream.applicable(program, domain, device_props)
+        ok, why = codegen_stream.applicable(program, domain, device_props, forced=True)
         if not ok:
             raise StencilException("strategy 'stream' cannot handle this stencil: " + why)
         return codegen_stream.make_plan(program, domain, device_props, options)

@@ -367,6 +367,8 @@ class ConcreteCudaStencil(object):
         self.module = compile_source(plan.source, "stencil_{}.cu".format(plan.strategy), plan.options)
         self.module.load()
         self._tmaps = {}
+        self._launches = {}
+        self._sc_launch = load_library().sc_launch
         self.last_kernel_ms = None
 
     # -- argument checks (the reference's ndpointer argtypes raise TypeError on mismatch)
@@ -403,28 +405,41 @@ class ConcreteCudaStencil(object):
                peer_pointer=0, peer_shift=0):
         """Enqueue the stencil over axis-0 range [a0_begin, a0_end) on ``stream``.  With
         ``peer_pointer`` every result is also stored at ``peer_pointer[flat_index + peer_shift]``
-        (a neighbouring slab's ghost planes, mapped peer memory)."""
+        (a neighbouring slab's ghost planes, mapped peer memory).  The marshalled argument block
+        of a (pointers, range) combination is cached: repeated sweeps cost one C call."""
         plan = self.plan
         lo, hi = plan.domain.sweep_range
         a0_begin = lo if a0_begin is None else a0_begin
         a0_end = hi if a0_end is None else a0_end
         if a0_end <= a0_begin:
             return
-        values = []
-        for info, pointer in zip(self.program.args, arg_pointers):
-            values.append(ctypes.c_void_p(pointer))
-        for spec in plan.tensor_maps:
-            values.append(self._tensor_map(spec, arg_pointers[spec.arg]))
-        values.append(ctypes.c_void_p(out_pointer))
-        values.append(ctypes.c_void_p(peer_pointer))
-        values.append(ctypes.c_longlong(peer_shift))
-        values.append(ctypes.c_int(a0_begin))
-        values.append(ctypes.c_int(a0_end))
-        geometry = plan.geometry(a0_begin, a0_end)
-        for extra in getattr(geometry, 'extra', ()):
-            values.append(ctypes.c_int(extra))
-        launch(self.module, plan.function, geometry, values,
-               self.device.stream if stream is None else stream)
+        key = (tuple(arg_pointers), out_pointer, a0_begin, a0_end, peer_pointer, peer_shift)
+        prepared = self._launches.get(key)
+        if prepared is None:
+            values = [ctypes.c_void_p(pointer) for pointer in arg_pointers]
+            for spec in plan.tensor_maps:
+                values.append(self._tensor_map(spec, arg_pointers[spec.arg]))
+            values.append(ctypes.c_void_p(out_pointer))
+            values.append(ctypes.c_void_p(peer_pointer))
+            values.append(ctypes.c_longlong(peer_shift))
+            values.append(ctypes.c_int(a0_begin))
+            values.append(ctypes.c_int(a0_end))
+            geometry = plan.geometry(a0_begin, a0_end)
+            for extra in getattr(geometry, 'extra', ()):
+                values.append(ctypes.c_int(extra))
+            pointers = (ctypes.c_void_p * len(values))(
+                *[ctypes.cast(ctypes.byref(v), ctypes.c_void_p) for v in values])
+            prepared = (values, pointers, (ctypes.c_uint32 * 3)(*geometry.grid),
+                        (ctypes.c_uint32 * 3)(*geometry.block), (ctypes.c_uint32 * 3)(*geometry.cluster),
+                        geometry.smem, plan.function.encode())
+            if len(self._launches) > 256:
+                self._launches.clear()
+            self._launches[key] = prepared
+        _, pointers, grid, block, cluster, smem, name = prepared
+        code = self._sc_launch(self.module.handle, name, grid, block, cluster, smem,
+                               self.device.stream if stream is None else stream, pointers)
+        if code != 0:
+            check(code, "launch of " + plan.function)
 
     # -- the call --------------------------------------------------------------------------------
     def __call__(self, *args, **kwargs):

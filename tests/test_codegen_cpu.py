@@ -12,6 +12,7 @@ from stencil_code_b200.stencil_kernel import StencilArgConfig
 from stencil_code_b200.stencil_exception import StencilException
 
 BIG_SHAPES = {1: (4096,), 2: (96, 256), 3: (24, 40, 128)}
+AUTO_STREAM_SHAPES = {2: (2048, 2048), 3: (128, 128, 256)}     # large enough for the planner to stream
 
 
 def make_plan(stencil, shapes_dtypes, strategy=None, **kwargs):
@@ -32,19 +33,31 @@ def arg_cfg_for(case, shape):
     return [(shape, numpy.float32)] + extra
 
 
-@pytest.mark.parametrize("strategy", ["direct", None])
+@pytest.mark.parametrize("strategy", ["direct", "stream"])
 @pytest.mark.parametrize("case,mode", CASE_MODE_PAIRS, ids=PAIR_IDS)
 def test_every_case_compiles_for_sm100a(case, mode, strategy, monkeypatch):
     monkeypatch.delenv("STENCIL_CUDA_STRATEGY", raising=False)
     stencil = case.make(mode, 'cuda')
-    shape = BIG_SHAPES[len(case.shape)] if strategy is None else case.shape
+    shape = BIG_SHAPES[len(case.shape)] if strategy == "stream" else case.shape
+    if strategy == "stream" and len(shape) == 1:
+        pytest.skip("rank 1 has no streaming generator")
     plan = make_plan(stencil, arg_cfg_for(case, shape), strategy)
-    if strategy is None and len(shape) > 1:
-        assert plan.strategy == 'stream', plan.notes
+    assert plan.strategy == strategy
     module = runtime.compile_source(plan.source, "cpu_check.cu", plan.options)
     assert module.cubin()[:4] == b"\x7fELF"
     launch = plan.geometry(*plan.domain.sweep_range)
     assert all(g >= 1 for g in launch.grid)
+
+
+def test_planner_picks_direct_for_small_and_stream_for_large(monkeypatch):
+    monkeypatch.delenv("STENCIL_CUDA_STRATEGY", raising=False)
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    from stencil_code_b200.library.simple import SimpleKernel
+    assert make_plan(SimpleKernel(), [((1024, 1024), numpy.float32)]).strategy == 'direct'
+    assert make_plan(SimpleKernel(), [(AUTO_STREAM_SHAPES[2], numpy.float32)]).strategy == 'stream'
+    assert make_plan(LaplacianKernel(), [((24, 40, 128), numpy.float32)]).strategy == 'direct'
+    assert make_plan(LaplacianKernel(), [(AUTO_STREAM_SHAPES[3], numpy.float32)]).strategy == 'stream'
+    assert make_plan(LaplacianKernel(), [((24, 40, 128), numpy.float64)]).strategy == 'direct'
 
 
 def test_literal_typing_and_exact_demotion():
@@ -78,10 +91,11 @@ def test_wrap_is_zero_as_in_the_reference():
     assert wrap.source == zero.source
 
 
-def test_planner_with_fake_device():
+def test_planner_with_fake_device(monkeypatch):
     from stencil_code_b200.library.laplacian import LaplacianKernel
     small = planner.DeviceProps(sm_count=4, smem_per_sm=64 * 1024, smem_per_block_optin=48 * 1024)
     cfg = [((512, 512, 512), numpy.float32)]
+    monkeypatch.delenv("STENCIL_CUDA_STRATEGY", raising=False)
     plan_small = make_plan(LaplacianKernel(), cfg, device_props=small)
     plan_b200 = make_plan(LaplacianKernel(), cfg)
     assert plan_small.notes['config']['smem_bytes'] <= 48 * 1024
