@@ -1,0 +1,459 @@
+"""Strategy 'temporal': two sweeps of an iterated rank-3 stencil fused into one pass over HBM.
+
+For ``stencil.iterate(grid, n)`` (Jacobi / Laplacian style iteration, SURVEY.md section 7 step 6;
+the idea of the reference's notebook ``ipython_notebooks/fusing_stencils``: keep the intermediate
+result of the first application on chip).  Per launch the kernel computes out = S(S(in)) with
+8 B of HBM traffic per point for TWO sweeps.
+
+Pipeline (extends ``codegen_stream``): the producer warp streams input planes of a tile through
+the TMA ring; consumer threads run sweep 1 from the rotating input register window and obtain the
+intermediate ("mid") plane z-1 for their own BY x 4 block.  Own mid values stay in a second
+register window (they are the z-1 / z / z+1 centre taps of sweep 2); the block is also written
+to one of three shared-memory mid buffers, a named barrier over the consumer warps follows, and
+sweep 2 reads its in-plane neighbours of the previous mid plane from shared memory and stores
+output plane z-2.  Tiles overlap: a CTA computes mid on MY x 128 points and outputs the interior
+(MY - 2*hy) x 120 of it, so no CTA needs another CTA's intermediate values.
+
+Boundary semantics are those of two consecutive sweeps: mid is subject to the same boundary
+handling as any sweep result ('zero'/'copy': halo selected at production; 'clamp': sweep 2 reads
+mid through the same clamped row offsets / column cascade as sweep 1 reads the input, and a
+uniform select substitutes the nearest in-grid mid plane along axis 0).  The arithmetic of both
+sweeps is the unchanged per-point program: results are bit-identical to two separate sweeps.
+
+Eligibility: rank 3, float32, exactly one grid argument, taps off the centre column only at
+dz = 0, |dz| <= 1, column radius <= 4, no data-indexed tables.
+"""
+import os
+
+from ...stencil_exception import StencilException
+from .. import point_program as pp
+from .codegen_common import PROLOGUE, emit_statements
+from .codegen_stream import (PTX_HELPERS, TensorMapSpec, Footprint, _Emitter, _group_loads, _tap3,
+                             _grid_args, table_plan, plan_chunks, _const_index, _LOCAL_NAME)
+
+FUNCTION = "stencil_temporal2"
+
+
+def eligible(program, domain):
+    if program.dim != 3 or program.out_ctype != pp.FLOAT:
+        return False, "rank 3 float32 only"
+    grids = _grid_args(program)
+    if len(grids) != 1 or grids[0].index != 0 or grids[0].ctype != pp.FLOAT:
+        return False, "exactly one float32 grid argument"
+    if program.shape[-1] % 4 or program.shape[-1] < 256 or program.shape[1] < 16 or program.shape[0] < 8:
+        return False, "grid too small or rows not 16-byte multiples"
+    if domain.is_slab:
+        return False, "slab domains exchange ghost planes every sweep"
+    data_tables = table_plan(program, False)[0]
+    if data_tables:
+        return False, "data-indexed tables"
+    if any(isinstance(s, pp.LocalAssign) for s in program.statements):
+        return False, "local temporaries"
+    ages = set()
+    for tap in program.taps():
+        dz, dy, dx = _tap3(tap.offset)
+        ages.add(dz)
+        if dz != 0 and (dy or dx):
+            return False, "taps off the centre column outside the middle plane"
+        if abs(dz) > 1 or abs(dx) > 4:
+            return False, "tap radius"
+    if ages != {-1, 0, 1}:
+        return False, "needs taps at dz = -1, 0, +1"
+    return True, "star-in-z rank-3 stencil"
+
+
+def _tag(v):
+    return "m{}".format(-v) if isinstance(v, int) and v < 0 else str(v)
+
+
+class TemporalConfig(object):
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def describe(self):
+        keys = ("MY", "BY", "NCW", "S", "HX", "HY", "OUT_ROWS", "OUT_COLS", "blocks_per_sm", "smem_bytes")
+        return dict({k: getattr(self, k) for k in keys}, strategy="temporal2")
+
+
+def choose_config(program, device_props):
+    lo, hi = program.tap_extent()
+    hx = max(-lo[2], hi[2])
+    hy = max(-lo[1], hi[1])
+    PADX = 4 if hx else 0
+    override = {}
+    for item in filter(None, os.environ.get("STENCIL_CUDA_TEMPORAL_TILE", "").split(",")):
+        key, _, value = item.partition("=")
+        override[key.strip()] = int(value)
+    best = None
+    for MY, BY, NCW, prefetch in ((32, 4, 8, 2), (64, 4, 16, 2), (32, 2, 16, 2), (16, 2, 8, 2)):
+        if override:
+            MY, BY, NCW = override.get("MY", MY), override.get("BY", BY), override.get("NCW", NCW)
+            prefetch = override.get("prefetch", prefetch)
+        if MY != BY * NCW or MY <= 2 * hy:
+            continue
+        S = 2 + prefetch
+        pitch = 128 + 2 * PADX
+        rows = MY + 2 * hy
+        stage_floats = (rows * pitch * 4 + 127) // 128 * 32
+        mid_floats = MY * 128
+        smem = S * stage_floats * 4 + (3 * mid_floats + 2 * 128) * 4 + 2 * S * 8 + 128
+        threads = (NCW + 1) * 32
+        if smem > device_props.smem_per_block_optin:
+            continue
+        blocks = min(device_props.smem_per_sm // (smem + 1024), device_props.max_threads_per_sm // threads, 4)
+        blocks = min(blocks, max(1, device_props.regs_per_sm // (threads * 128)))
+        if blocks < 1:
+            continue
+        out_rows, out_cols = MY - 2 * hy, 128 - (8 if hx else 0)
+        # traffic per output point of the pair of sweeps, and redundant sweep-1 work
+        traffic = rows * (pitch + 8) / float(out_rows * out_cols) + 1.0
+        redundancy = MY * 128 / float(out_rows * out_cols)
+        score = traffic * (1.0 + 0.15 * (redundancy - 1.0)) * (1.0 if blocks * NCW >= 16 else 1.08)
+        config = TemporalConfig(MY=MY, BY=BY, NCW=NCW, S=S, HX=hx, HY=hy, PADX=PADX, PITCH=pitch, ROWS=rows,
+                                STAGE_FLOATS=stage_floats, STAGE_BYTES=rows * pitch * 4, MID_FLOATS=mid_floats,
+                                OUT_ROWS=out_rows, OUT_COLS=out_cols, smem_bytes=smem, threads=threads,
+                                blocks_per_sm=blocks, score=score)
+        if best is None or score < best.score:
+            best = config
+        if override:
+            break
+    if best is None:
+        raise StencilException("no temporal tile fits in shared memory")
+    return best
+
+
+def generate(program, domain, cfg):
+    shape = program.shape
+    N0, N1, N2 = shape
+    MY, BY, NCW, S = cfg.MY, cfg.BY, cfg.NCW, cfg.S
+    HX, HY, PADX, PITCH = cfg.HX, cfg.HY, cfg.PADX, cfg.PITCH
+    SF, MF = cfg.STAGE_FLOATS, cfg.MID_FLOATS
+    MP = 128                                  # mid buffer pitch
+    boundary = program.boundary
+    clamp, copy = boundary == 'clamp', boundary == 'copy'
+    c_lo, c_hi = domain.clamp_lo, domain.clamp_hi
+    i_lo, i_hi = domain.interior_lo, domain.interior_hi
+    fp = Footprint(program, BY, copy)
+    _, const_refs, _, _ = table_plan(program, False)
+    clamp_rows = clamp and HY > 0
+    clamp_cols = clamp and HX > 0
+    W = 3
+
+    def in_slot(phase, age, key):
+        ages = fp.ages[key]
+        if max(ages) == min(ages):
+            return 0
+        return (phase + age - 1) % W
+
+    def in_name(phase, age, row, col):
+        return "i{}_{}_{}".format(in_slot(phase, age, (0, row, col)), _tag(row), _tag(col))
+
+    def mid_own(phase, age, b, j):
+        """own mid value of the plane with `age` relative to the OUTPUT plane (computed at unit-1+age)"""
+        return "m{}_{}_{}".format((phase + age - 1) % W, b, j)
+
+    def table_text(ref, index_text):
+        return "tc{}_{}".format(ref.arg, _const_index(ref.index))
+
+    e = _Emitter()
+    e.lines.append(PROLOGUE)
+    e.lines.append(PTX_HELPERS.replace("@STOP@", os.environ.get("STENCIL_CUDA_STORE_OP", ".cs")))
+    e("// temporal strategy: two fused sweeps | grid {} boundary {} | mid tile {}x128, output {}x{}, "
+      "BY={} ring S={}".format(shape, boundary, MY, cfg.OUT_ROWS, cfg.OUT_COLS, BY, S))
+    params = ["const {}* __restrict__ a{}".format(arg.ctype, arg.index) for arg in program.args]
+    params += ["const __grid_constant__ TensorMap tm0", "float* __restrict__ out",
+               "int a0_begin", "int a0_end", "int chunk_len"]
+    e('extern "C" __global__ void __launch_bounds__({}, {})'.format(cfg.threads, cfg.blocks_per_sm))
+    e("{}({})".format(FUNCTION, ", ".join(params)))
+    e.open("")
+    e("extern __shared__ __align__(128) unsigned char smem_raw[];")
+    e("float* const ring = reinterpret_cast<float*>(smem_raw);")
+    e("float* const mid = ring + {} + 128;        // three mid buffers, one pad row on either side".format(S * SF))
+    e("u64* const bar_full = reinterpret_cast<u64*>(smem_raw + {});".format((S * SF + 3 * MF + 2 * 128) * 4))
+    e("u64* const bar_empty = bar_full + {};".format(S))
+    e("const int tid = threadIdx.x;")
+    e("const int warp = tid >> 5;")
+    e("const int lane = tid & 31;")
+    e("const int x0 = blockIdx.x * {} - {};     // origin of the mid tile (outputs are its interior)".format(
+        cfg.OUT_COLS, PADX))
+    e("const int y0 = blockIdx.y * {} - {};".format(cfg.OUT_ROWS, HY))
+    e("const int u_begin = a0_begin + blockIdx.z * chunk_len;")
+    e("const int u_end = min(u_begin + chunk_len, a0_end);")
+    e("if (u_begin >= u_end) return;")
+    e("const int p_first = u_begin - 2;             // axis-0 index of streamed input plane 0")
+    e("const int n_units = (u_end - u_begin) + 4;")
+    e.open("if (tid == 0)")
+    e.open("for (int s = 0; s < {}; ++s)".format(S))
+    e("mbar_init(&bar_full[s], 1);")
+    e("mbar_init(&bar_empty[s], {});".format(NCW))
+    e.close()
+    e("fence_barrier_init();")
+    e.close()
+    e("__syncthreads();")
+    e()
+    # ------------------------------------------------------------------ producer
+    e.open("if (warp == {})".format(NCW))
+    e("if (lane == 0) tma_prefetch_desc(&tm0);")
+    e.open("for (int k = 0; k < n_units; ++k)")
+    e("const int s = k % {};".format(S))
+    e("if (k >= {S}) mbar_wait(&bar_empty[s], ((k / {S}) - 1) & 1);".format(S=S))
+    e.open("if (lane == 0)")
+    e("mbar_expect_tx(&bar_full[s], {});".format(cfg.STAGE_BYTES))
+    e("tma_load_3d(ring + s * {sf}, &tm0, &bar_full[s], x0 - {px}, y0 - {hy}, SC_CLAMP(p_first + k, {lo}, {hi}));".format(
+        sf=SF, px=PADX, hy=HY, lo=c_lo[0], hi=c_hi[0]))
+    e.close()
+    e.close()
+    e("return;")
+    e.close()
+    e()
+    # ------------------------------------------------------------------ consumers
+    e("const int tr = warp;")
+    e("const int gy = y0 + tr * {};               // first row of this thread's block".format(BY))
+    e("const int gx = x0 + lane * 4;             // first column of this thread's block")
+    e("const int sbase_in = ({} + tr * {}) * {} + {} + lane * 4;".format(HY, BY, PITCH, PADX))
+    e("const int sbase_mid = tr * {} * {} + lane * 4;".format(BY, MP))
+    rows_needed = sorted({k[1] for k in fp.ages})
+    if clamp_rows:
+        for row in rows_needed:
+            e("const int rd{t} = min(max(gy + ({r}), 0), {n}) - (gy + ({r}));   // clamped row delta".format(
+                t=_tag(row), r=row, n=N1 - 1))
+    if clamp_cols:
+        e("const bool x_edge = x0 <= 0 || x0 + {} > {};".format(128 + HX, N2))
+    if not clamp:
+        e("u32 halo_mask = 0;                   // bit (b*4+j): the point lies in the in-plane halo")
+        for b in range(BY):
+            for j in range(4):
+                tests = []
+                if i_lo[1] > 0:
+                    tests.append("gy + {} < {}".format(b, i_lo[1]))
+                if i_hi[1] < N1:
+                    tests.append("gy + {} >= {}".format(b, i_hi[1]))
+                if i_lo[2] > 0:
+                    tests.append("gx + {} < {}".format(j, i_lo[2]))
+                if i_hi[2] < N2:
+                    tests.append("gx + {} >= {}".format(j, i_hi[2]))
+                if tests:
+                    e("if ({}) halo_mask |= {}u;".format(" || ".join(tests), 1 << (b * 4 + j)))
+    # which of this thread's outputs are inside the valid (interior) part of the mid tile and the grid
+    lane_ok = "lane >= 1 && lane <= 30 && " if HX else ""
+    e("const bool col_ok = {}gx >= 0 && gx < {};".format(lane_ok, N2))
+    for (arg, index), ctype in sorted(const_refs.items()):
+        e("const {} tc{}_{} = a{}[{}];".format(ctype, arg, index, arg, index))
+    names = []
+    for (g, row, col), ages in sorted(fp.ages.items()):
+        slots = W if max(ages) > min(ages) else 1
+        names += ["i{}_{}_{}".format(slot, _tag(row), _tag(col)) for slot in range(slots)]
+    names += ["m{}_{}_{}".format(slot, b, j) for slot in range(W) for b in range(BY) for j in range(4)]
+    for first in range(0, len(names), 8):
+        e("float {};".format(", ".join(n + " = 0.0f" for n in names[first:first + 8])))
+    counter = [0]
+
+    def column_fix(names_by_col):
+        for c in sorted((c for c in names_by_col if c < 0), reverse=True):
+            e("if (gx + ({}) < 0) {} = {};".format(c, names_by_col[c], names_by_col[c + 1]))
+        for c in sorted(c for c in names_by_col if c > 3):
+            e("if (gx + {} > {}) {} = {};".format(c, N2 - 1, names_by_col[c], names_by_col[c - 1]))
+
+    def load_rows(pointer, pitch, by_row, name_of_col, declare):
+        """vectorised shared-memory loads of {row: cols} relative to the thread's block"""
+        for row in sorted(by_row):
+            for first, width, used in _group_loads(by_row[row]):
+                offset = "{}".format(row * pitch + first)
+                if clamp_rows:
+                    offset = "rd{} * {} + ({})".format(_tag(row), pitch, offset)
+                if width == 1:
+                    e("{}{} = {}[{}];".format(declare, name_of_col(row, used[0]), pointer, offset))
+                    continue
+                counter[0] += 1
+                tmp = "q{}".format(counter[0])
+                vec = "float4" if width == 4 else "float2"
+                e("const {v} {t} = *reinterpret_cast<const {v}*>({p} + ({o}));".format(v=vec, t=tmp, p=pointer, o=offset))
+                e(" ".join("{}{} = {}.{};".format(declare, name_of_col(row, c), tmp, "xyzw"[c - first]) for c in used))
+
+    e("int unit = 0;                        // newest streamed input plane, relative to p_first")
+    e.open("while (true)")
+    for phase in range(W):
+        e("// ---- window phase {}".format(phase))
+        e("if (unit >= n_units) break;")
+        e.open("")
+        e("mbar_wait(&bar_full[unit % {S}], (unit / {S}) & 1);".format(S=S))
+        # ---------------- sweep-1 input window (same scheme as codegen_stream, regwin)
+        reads = {}
+        for key, ages in fp.ages.items():
+            reads.setdefault(max(ages), []).append(key)
+        for age in sorted(reads):
+            back = 1 - age
+            e("const float* const uI{t} = ring + ((unit + {k} - {b}) % {S}) * {sf} + sbase_in;".format(
+                t=_tag(age), k=3 * S, b=back, S=S, sf=SF))
+        for age in sorted(reads):
+            by_row = {}
+            for (_, row, col) in reads[age]:
+                by_row.setdefault(row, set()).add(col)
+            load_rows("uI{}".format(_tag(age)), PITCH, by_row,
+                      lambda row, col, age=age: in_name(phase, age, row, col), "")
+            if clamp_cols and any(c < 0 or c > 3 for cols in by_row.values() for c in cols):
+                e.open("if (x_edge)")
+                for row in sorted(by_row):
+                    outer = [c for c in by_row[row] if c < 0 or c > 3]
+                    if outer:
+                        span = range(min(min(outer), 0), max(max(outer), 3) + 1)
+                        column_fix({c: in_name(phase, age, row, c) for c in span if (0, row, c) in fp.ages})
+                e.close()
+        release_back = 1 - min(max(s) for s in fp.ages.values())
+        e("__syncwarp();")
+        e("if (lane == 0 && unit >= {b}) mbar_arrive(&bar_empty[(unit - {b}) % {S}]);".format(b=release_back, S=S))
+
+        # ---------------- sweep 1: mid plane zm = p_first + unit - 1
+        e.open("if (unit >= 2)")
+        e("const int zm = p_first + unit - 1;")
+        macc = [["ma{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
+        for b in range(BY):
+            e("float {};".format(", ".join(n + " = 0.0f" for n in macc[b])))
+        for statement in program.statements:
+            for b in range(BY):
+                for j in range(4):
+                    def tap_text(tap, b=b, j=j):
+                        dz, dy, dx = _tap3(tap.offset)
+                        return in_name(phase, dz, b + dy, j + dx)
+                    single = pp.PointProgram(3, shape, program.out_ctype, program.args, [statement],
+                                             program.ghost_depth, boundary)
+                    e(emit_statements(single, tap_text, table_text, acc=macc[b][j], indent="")[0])
+        if not clamp:
+            ztests = []
+            if i_lo[0] > 0:
+                ztests.append("zm < {}".format(i_lo[0]))
+            if i_hi[0] < N0:
+                ztests.append("zm >= {}".format(i_hi[0]))
+            e("const bool zm_halo = {};".format(" || ".join(ztests) if ztests else "false"))
+            e.open("if (zm_halo || halo_mask)")
+            for b in range(BY):
+                for j in range(4):
+                    value = in_name(phase, 0, b, j) if copy else "0.0f"
+                    e("if (zm_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), macc[b][j], value))
+            e.close()
+        e("float* const mid_new = mid + (unit % 3) * {} + sbase_mid;".format(MF))
+        for b in range(BY):
+            for j in range(4):
+                e("{} = {};".format(mid_own(phase, 1, b, j), macc[b][j]))
+            e("*reinterpret_cast<float4*>(mid_new + {}) = make_float4({});".format(b * MP, ", ".join(macc[b])))
+        e('asm volatile("bar.sync 1, {};" ::: "memory");'.format(NCW * 32))
+
+        # ---------------- sweep 2: output plane zo = p_first + unit - 2
+        e.open("if (unit >= 4)")
+        e("const int zo = p_first + unit - 2;")
+        e("const float* const uM = mid + ((unit + 2) % 3) * {} + sbase_mid;   // mid plane zo".format(MF))
+        # in-plane taps of sweep 2.  A tap in the point's own row and own quad is the thread's own
+        # mid register.  Everything else is read from the mid buffer; under 'clamp' that includes
+        # other rows of the thread's own block, because a block row outside the grid must read as
+        # the clamped row (the buffer read goes through the clamped row offset, a register would not)
+        by_row = {}
+        for tap in program.taps():
+            dz, dy, dx = _tap3(tap.offset)
+            if dz != 0:
+                continue
+            for b in range(BY):
+                for j in range(4):
+                    row, col = b + dy, j + dx
+                    own = 0 <= col < 4 and (dy == 0 if clamp else 0 <= row < BY)
+                    if not own:
+                        by_row.setdefault(row, set()).add(col)
+        if clamp_cols:
+            for row, cols in by_row.items():       # the select cascade needs every column up to the quad
+                if min(cols) < 0:
+                    cols.update(range(min(cols), 0))
+                if max(cols) > 3:
+                    cols.update(range(4, max(cols) + 1))
+
+        def nb_name(row, col, same_row=False):
+            own = 0 <= col < 4 and (same_row if clamp else 0 <= row < BY)
+            if own:
+                return mid_own(phase, 0, row, col)
+            return "n_{}_{}".format(_tag(row), _tag(col))
+        load_rows("uM", MP, by_row, nb_name, "float ")
+        if clamp_cols and any(c < 0 or c > 3 for cols in by_row.values() for c in cols):
+            e.open("if (x_edge)")
+            for row in sorted(by_row):
+                outer = [c for c in by_row[row] if c < 0 or c > 3]
+                if outer:
+                    # the cascade starts from the thread's own quad: columns 0 and 3 of this row,
+                    # loaded from the buffer if the row is not the point's own, else the register
+                    names = {c: nb_name(row, c) for c in outer}
+                    for c in (0, 3):
+                        names[c] = ("n_{}_{}".format(_tag(row), c) if c in by_row[row]
+                                    else mid_own(phase, 0, row, c))
+                    column_fix(names)
+            e.close()
+        if clamp:
+            e("const bool z_lo = zo - 1 < {};   // axis-0 clamp of the intermediate grid".format(c_lo[0]))
+            e("const bool z_hi = zo + 1 > {};".format(c_hi[0]))
+        acc = [["acc{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
+        for b in range(BY):
+            e("float {};".format(", ".join(n + " = 0.0f" for n in acc[b])))
+        for statement in program.statements:
+            for b in range(BY):
+                for j in range(4):
+                    def tap_text(tap, b=b, j=j):
+                        dz, dy, dx = _tap3(tap.offset)
+                        if dz == 0:
+                            return nb_name(b + dy, j + dx, same_row=(dy == 0))
+                        own = mid_own(phase, dz, b, j)
+                        if clamp:
+                            return "({} ? {} : {})".format("z_lo" if dz < 0 else "z_hi", mid_own(phase, 0, b, j), own)
+                        return own
+                    single = pp.PointProgram(3, shape, program.out_ctype, program.args, [statement],
+                                             program.ghost_depth, boundary)
+                    e(emit_statements(single, tap_text, table_text, acc=acc[b][j], indent="")[0])
+        if not clamp:
+            ztests = []
+            if i_lo[0] > 0:
+                ztests.append("zo < {}".format(i_lo[0]))
+            if i_hi[0] < N0:
+                ztests.append("zo >= {}".format(i_hi[0]))
+            e("const bool zo_halo = {};".format(" || ".join(ztests) if ztests else "false"))
+            e.open("if (zo_halo || halo_mask)")
+            for b in range(BY):
+                for j in range(4):
+                    # 'copy': the halo of sweep 2 copies the halo of mid, which copied the input
+                    value = mid_own(phase, 0, b, j) if copy else "0.0f"
+                    e("if (zo_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), acc[b][j], value))
+            e.close()
+        for b in range(BY):
+            row_ok = "tr * {by} + {b} >= {hy} && tr * {by} + {b} < {hi} && gy + {b} >= 0 && gy + {b} < {n1}".format(
+                by=BY, b=b, hy=HY, hi=MY - HY, n1=N1)
+            e("if (col_ok && {}) st_global_v4(out + ((i64)zo * {} + (gy + {})) * {} + gx, {});".format(
+                row_ok, N1, b, N2, ", ".join(acc[b])))
+        e.close()   # unit >= 4
+        e.close()   # unit >= 2
+        e("++unit;")
+        e.close()
+    e.close()   # while
+    e.close()   # kernel
+    return e.text()
+
+
+def make_plan(program, domain, device_props, options):
+    """CudaPlan-like record for the fused two-sweep kernel (launched by ``iterate``)."""
+    from .transformer import CudaPlan
+    from .planner import Launch
+    ok, why = eligible(program, domain)
+    if not ok:
+        raise StencilException("temporal blocking not applicable: " + why)
+    cfg = choose_config(program, device_props)
+    source = generate(program, domain, cfg)
+    n0, n1, n2 = program.shape
+    specs = [TensorMapSpec(0, (n2, n1, n0), (n2 * 4, n1 * n2 * 4), (cfg.PITCH, cfg.ROWS, 1), tag="temporal")]
+    tiles_x = -(-n2 // cfg.OUT_COLS)
+    tiles_y = -(-n1 // cfg.OUT_ROWS)
+    slots = device_props.sm_count * cfg.blocks_per_sm
+
+    def geometry(a0_begin, a0_end):
+        n_units = a0_end - a0_begin
+        chunks = plan_chunks(n_units, tiles_x * tiles_y, slots, 5, 32)
+        chunk_len = -(-n_units // chunks)
+        chunks = -(-n_units // chunk_len)
+        launch = Launch((tiles_x, tiles_y, chunks), (cfg.threads, 1, 1), cfg.smem_bytes)
+        launch.extra = (chunk_len,)
+        return launch
+
+    return CudaPlan(program, domain, 'temporal', source, FUNCTION, options, geometry,
+                    tensor_maps=specs, notes={'config': cfg.describe()})

@@ -368,6 +368,7 @@ class ConcreteCudaStencil(object):
         self.module.load()
         self._tmaps = {}
         self._launches = {}
+        self._temporal = None
         self._sc_launch = load_library().sc_launch
         self.last_kernel_ms = None
 
@@ -407,21 +408,26 @@ class ConcreteCudaStencil(object):
         ``peer_pointer`` every result is also stored at ``peer_pointer[flat_index + peer_shift]``
         (a neighbouring slab's ghost planes, mapped peer memory).  The marshalled argument block
         of a (pointers, range) combination is cached: repeated sweeps cost one C call."""
-        plan = self.plan
+        self._launch_plan(self.plan, self.module, arg_pointers, out_pointer, a0_begin, a0_end, stream,
+                          peer_pointer, peer_shift)
+
+    def _launch_plan(self, plan, module, arg_pointers, out_pointer, a0_begin, a0_end, stream,
+                     peer_pointer=0, peer_shift=0):
         lo, hi = plan.domain.sweep_range
         a0_begin = lo if a0_begin is None else a0_begin
         a0_end = hi if a0_end is None else a0_end
         if a0_end <= a0_begin:
             return
-        key = (tuple(arg_pointers), out_pointer, a0_begin, a0_end, peer_pointer, peer_shift)
+        key = (plan.strategy, tuple(arg_pointers), out_pointer, a0_begin, a0_end, peer_pointer, peer_shift)
         prepared = self._launches.get(key)
         if prepared is None:
             values = [ctypes.c_void_p(pointer) for pointer in arg_pointers]
             for spec in plan.tensor_maps:
                 values.append(self._tensor_map(spec, arg_pointers[spec.arg]))
             values.append(ctypes.c_void_p(out_pointer))
-            values.append(ctypes.c_void_p(peer_pointer))
-            values.append(ctypes.c_longlong(peer_shift))
+            if plan.strategy != 'temporal':
+                values.append(ctypes.c_void_p(peer_pointer))
+                values.append(ctypes.c_longlong(peer_shift))
             values.append(ctypes.c_int(a0_begin))
             values.append(ctypes.c_int(a0_end))
             geometry = plan.geometry(a0_begin, a0_end)
@@ -436,7 +442,7 @@ class ConcreteCudaStencil(object):
                 self._launches.clear()
             self._launches[key] = prepared
         _, pointers, grid, block, cluster, smem, name = prepared
-        code = self._sc_launch(self.module.handle, name, grid, block, cluster, smem,
+        code = self._sc_launch(module.handle, name, grid, block, cluster, smem,
                                self.device.stream if stream is None else stream, pointers)
         if code != 0:
             check(code, "launch of " + plan.function)
@@ -543,6 +549,40 @@ class ConcreteCudaStencil(object):
             buffer.release()
         return result
 
+    # -- temporal blocking ----------------------------------------------------------------------
+    def temporal(self):
+        """(plan, module) of the fused two-sweep kernel, or None when the stencil is not eligible
+        (or STENCIL_CUDA_TEMPORAL=0)."""
+        if self._temporal is None:
+            self._temporal = False
+            if os.environ.get("STENCIL_CUDA_TEMPORAL", "1") not in ("0", ""):
+                from . import codegen_temporal
+                ok, _ = codegen_temporal.eligible(self.program, self.plan.domain)
+                if ok and self.plan.strategy == 'stream':
+                    plan = codegen_temporal.make_plan(self.program, self.plan.domain,
+                                                      self.device.planner_props(), self.plan.options)
+                    module = compile_source(plan.source, "stencil_temporal.cu", plan.options)
+                    module.load()
+                    self._temporal = (plan, module)
+        return self._temporal or None
+
+    def sweeps(self, pointers_a, pointer_b, table_pointers, count, stream):
+        """``count`` sweeps ping-ponging between device buffers a and b (a holds the input).
+        Pairs of sweeps run as one fused launch where temporal blocking applies.  Returns the
+        pointer that holds the result."""
+        current, spare = pointers_a, pointer_b
+        fused = self.temporal()
+        remaining = count
+        while remaining > 0:
+            if fused is not None and remaining >= 2:
+                self._launch_plan(fused[0], fused[1], [current] + table_pointers, spare, None, None, stream)
+                remaining -= 2
+            else:
+                self.launch([current] + table_pointers, spare, stream=stream)
+                remaining -= 1
+            current, spare = spare, current
+        return current
+
     # -- iterated application -------------------------------------------------------------------
     def iterate(self, grid, iterations, *tables, **kwargs):
         """``iterations`` sweeps ``g = stencil(g, *tables)`` with the grid resident on the device
@@ -557,15 +597,26 @@ class ConcreteCudaStencil(object):
             import torch
             stream = ctypes.c_void_p(torch.cuda.current_stream(grid.device).cuda_stream)
             tensors = [t.contiguous() for t in args]
-            current = tensors[0]
-            spare = torch.empty_like(current)
-            result = None
-            for _ in range(iterations):
-                self.launch([current.data_ptr()] + [t.data_ptr() for t in tensors[1:]],
-                            spare.data_ptr(), stream=stream)
-                current, spare = spare, (current if current is not tensors[0] else torch.empty_like(current))
-                result = current
-            return grid.clone() if result is None else result
+            if iterations == 0:
+                return grid.clone()
+            first = torch.empty_like(tensors[0])
+            second = torch.empty_like(tensors[0]) if iterations > 1 else None
+            tables_ptr = [t.data_ptr() for t in tensors[1:]]
+            # the caller's grid is never written: the first (pair of) sweep(s) reads it directly
+            fused = self.temporal()
+            if fused is not None and iterations >= 2:
+                self._launch_plan(fused[0], fused[1], [tensors[0].data_ptr()] + tables_ptr, first.data_ptr(),
+                                  None, None, stream)
+                done = 2
+            else:
+                self.launch([tensors[0].data_ptr()] + tables_ptr, first.data_ptr(), stream=stream)
+                done = 1
+            if done == iterations:
+                return first
+            if second is None:
+                second = torch.empty_like(first)
+            result = self.sweeps(first.data_ptr(), second.data_ptr(), tables_ptr, iterations - done, stream)
+            return first if result == first.data_ptr() else second
         check(library.sc_set_device(device.index))
         stream = device.stream
         arrays = [numpy.ascontiguousarray(a) for a in args]
@@ -574,10 +625,8 @@ class ConcreteCudaStencil(object):
         for array, buffer in zip(arrays, buffers):
             check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(array.ctypes.data),
                                               array.nbytes, stream))
-        current = buffers[0]
-        for _ in range(iterations):
-            self.launch([current.ptr] + [b.ptr for b in buffers[1:]], spare.ptr, stream=stream)
-            current, spare = spare, current
+        final = self.sweeps(buffers[0].ptr, spare.ptr, [b.ptr for b in buffers[1:]], iterations, stream)
+        current, spare = (buffers[0], spare) if final == buffers[0].ptr else (spare, buffers[0])
         result = device.pinned_empty(arrays[0].shape, arrays[0].dtype)
         check(library.sc_memcpy_d2h_async(ctypes.c_void_p(result.ctypes.data), ctypes.c_void_p(current.ptr),
                                           result.nbytes, stream))

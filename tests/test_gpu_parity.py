@@ -191,3 +191,35 @@ def test_pipelined_host_path_matches_oracle():
             expected = oracle_output(make('python', mode), numpy.array(pinned), variant='c_parallel')
             assert_bit_identical(numpy.array(make('cuda', mode)(pinned)), expected)
             assert_bit_identical(numpy.array(make('cuda', mode)(numpy.array(pinned))), expected)   # pageable
+
+
+TEMPORAL_SHAPES = [(12, 70, 256), (19, 64, 388), (33, 100, 260), (9, 31, 512)]
+
+
+@pytest.mark.parametrize("mode", ["clamp", "zero", "copy"])
+@pytest.mark.parametrize("shape", TEMPORAL_SHAPES, ids=["x".join(map(str, s)) for s in TEMPORAL_SHAPES])
+def test_temporal_blocking_equals_separate_sweeps(mode, shape, monkeypatch):
+    """iterate() fuses pairs of sweeps into one kernel (codegen_temporal); the result must be
+    bit-identical to sweeping n times -- checked against the CPU oracle applied n times."""
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    monkeypatch.delenv("STENCIL_CUDA_TEMPORAL", raising=False)
+    monkeypatch.setenv("STENCIL_CUDA_STRATEGY", "stream")
+    for make in (lambda backend: Jacobi3D(1.0, 0.25, backend=backend, boundary_handling=mode),
+                 lambda backend: LaplacianKernel(backend=backend, boundary_handling=mode)):
+        grid = numpy.random.RandomState(17).random_sample(shape).astype(numpy.float32)
+        stencil = make('cuda')
+        concrete = stencil.specializer.specialize((grid,))
+        assert concrete.temporal() is not None, "temporal kernel expected for this stencil"
+        python_side = make('python')
+        expected = grid
+        for sweeps in (1, 2, 3, 4, 5):
+            expected = oracle_output(python_side, expected)
+            if sweeps in (2, 3, 5):
+                assert_bit_identical(stencil.iterate(grid, sweeps), expected)
+    import torch
+    tensor = torch.from_numpy(grid).cuda()
+    assert_bit_identical(stencil.iterate(tensor, 4).cpu().numpy(),
+                         oracle_output(python_side, oracle_output(python_side, oracle_output(
+                             python_side, oracle_output(python_side, grid)))))
+    assert_bit_identical(tensor.cpu().numpy(), grid)          # the caller's tensor is not modified

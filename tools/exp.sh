@@ -1,8 +1,5 @@
-P="python tools/probe.py"
-$P conv5 clamp 10
-STENCIL_CUDA_FIX_BRANCH=0 $P conv5 clamp 10
-$P laplacian512 clamp 20
-STENCIL_CUDA_FIX_BRANCH=0 $P laplacian512 clamp 20
-STENCIL_CUDA_FIX_BRANCH=100 $P laplacian512 clamp 20
-$P jacobi3d clamp 10
-STENCIL_CUDA_FIX_BRANCH=0 $P jacobi3d clamp 10
+python tools/probe_iter.py 512x1024x1024 20
+STENCIL_CUDA_TEMPORAL=0 python tools/probe_iter.py 512x1024x1024 20
+STENCIL_CUDA_TEMPORAL_TILE="MY=32,BY=4,NCW=8" python tools/probe_iter.py 512x1024x1024 20
+STENCIL_CUDA_TEMPORAL_TILE="MY=64,BY=4,NCW=16" python tools/probe_iter.py 512x1024x1024 20
+python tools/probe_iter.py 512x1024x1024 20 copy
