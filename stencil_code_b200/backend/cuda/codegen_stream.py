@@ -334,9 +334,12 @@ def choose_config(program, domain, device_props, override=None):
         fill = items / float(-(-items // slots) * slots)
         resident_warps = blocks_per_sm * cand['NCW']
         score = waste * (1.0 + read_factor) / 2.0 / (fill ** 0.5) * (1.0 if resident_warps >= 12 else 1.1)
-        if 8.0 * program.npoints < 4e9:
-            # measured on B200 (profiles/): sweeps of a few hundred microseconds are ramp/tail
-            # dominated and run 3-6 % faster with more, smaller CTAs per SM than the traffic model says
+        if tiles < slots / 2:
+            # measured on B200: when a plane has far fewer tiles than there are resident CTA slots
+            # (512^2 planes: 32 tiles of 64x128 for 148 slots) the sweep needs many axis-0 chunks
+            # per tile and runs 5-10 % faster with more, smaller CTAs per SM than the traffic model
+            # says (Laplacian 512^3: 690 vs 620 GStencil/s); with 128 tiles per plane
+            # (256x1024x1024) the big tile wins (770 vs 679)
             score *= {1: 1.10, 2: 1.04}.get(blocks_per_sm, 1.0)
         if embedded:
             score = float(len(candidates) - candidates.index(cand)) * -1.0      # first that fits wins

@@ -4,7 +4,7 @@ The reference has no multi-device path at all; this is the north-star's addition
 sweeps (Jacobi-3D).  One process per GPU.  The global grid is cut along axis 0 into contiguous
 slabs; every rank's local array carries ``h`` ghost planes on both sides (``h`` = ghost depth along
 axis 0).  A sweep on one rank is three launches of the SAME generated kernel over axis-0
-sub-ranges, all on one stream:
+sub-ranges (1-3 on an edge stream, 4 on the main stream, overlapping; see ``iterate``):
 
   1. top boundary planes    -> local result AND, through a peer-mapped pointer, straight into the
   2. bottom boundary planes    neighbour's ghost planes (NVLink stores issued by the stencil kernel
@@ -117,6 +117,10 @@ class SlabStencil(object):
             self.table_buffers.append(buffer)
         self.device.synchronize()
         self.sweep = 0
+        self.edge_stream = self.device._new_stream()
+        self.edge_done = self.device.new_event()
+        self.interior_done = self.device.new_event()
+        self._events_armed = False
         self.peers = {}
         if slab.ghosted:
             self._open_peers()
@@ -171,6 +175,7 @@ class SlabStencil(object):
 
     def load(self, global_grid):
         """Copy this rank's planes (plus ghost planes) of a host array of the global shape."""
+        self.synchronize()
         slab = self.slab
         lo = max(0, slab.start - slab.first_real)
         hi = min(slab.global_shape[0], slab.stop + (slab.h if slab.ghosted else 0))
@@ -185,6 +190,7 @@ class SlabStencil(object):
 
     def result(self):
         """This rank's real planes as a host array."""
+        self.synchronize()
         slab = self.slab
         shape = (slab.planes,) + slab.global_shape[1:]
         out = self.device.pinned_empty(shape, numpy.float32)
@@ -197,6 +203,7 @@ class SlabStencil(object):
     def checksum(self):
         """Position-dependent 64-bit checksum of the real planes; summed (mod 2^64) over ranks it
         is independent of the decomposition."""
+        self.synchronize()
         slab = self.slab
         count = slab.planes * slab.plane_elems
         cell = self.device.alloc(256)
@@ -221,42 +228,70 @@ class SlabStencil(object):
 
     # -- sweeps ------------------------------------------------------------------------------------
     def iterate(self, sweeps):
-        """Enqueue ``sweeps`` sweeps on this rank's stream (asynchronous; see ``synchronize``)."""
+        """Enqueue ``sweeps`` sweeps (asynchronous; see ``synchronize``).
+
+        Two streams per rank: the *edge* stream runs the boundary-plane launches (which also store
+        into the neighbours' ghost planes) and the flag signal, the main stream runs the interior
+        launch; both read the current buffer and write disjoint planes of the next one, so they
+        overlap.  Hazards between sweeps are closed by two events and the neighbours' flags:
+
+          * edge(t) waits interior(t-1): it reads planes the interior wrote, and writes planes of
+            the buffer interior(t-1) was still reading;
+          * interior(t) waits edge(t-1): same two reasons, mirrored;
+          * edge(t) waits for both neighbours' flags >= t-1: their boundary results of sweep t-1
+            are in my ghost planes, and they are done reading the ghost planes I am about to
+            overwrite (ghost planes are only ever read by edge kernels).
+        """
         slab = self.slab
-        runtime, library, stream = self.runtime, self.library, self.device.stream
+        runtime, library = self.runtime, self.library
+        main, edge = self.device.stream, self.edge_stream
         tables = [b.ptr for b in self.table_buffers]
         top, interior, bottom = slab.ranges()
         up, down = self.peers.get(slab.rank - 1), self.peers.get(slab.rank + 1)
         plane = slab.plane_elems
         signal_geometry = type("L", (), dict(grid=(1, 1, 1), block=(32, 1, 1), cluster=(1, 1, 1), smem=0))()
+        exchanging = bool(up or down)
         for _ in range(sweeps):
             number = self.sweep + 1
             current = self.buffers[self.sweep % 2].ptr
             target_index = (self.sweep + 1) % 2
             target = self.buffers[target_index].ptr
-            # ghost planes of `current` were written by the neighbours during sweep number-1
-            # (initial ghosts come from load()/fill_uniform()).  Flags: [0] from up, [1] from down.
-            if number > 1:
+            if exchanging:
+                if number > 1 or self._events_armed:
+                    runtime.check(library.sc_stream_wait_event(edge, self.interior_done))
+                    runtime.check(library.sc_stream_wait_event(main, self.edge_done))
+                if number > 1:
+                    # flags: [0] written by the upper neighbour, [1] by the lower one
+                    if up:
+                        runtime.check(library.sc_stream_wait_value32(edge, ctypes.c_void_p(self.flags.ptr), number - 1))
+                    if down:
+                        runtime.check(library.sc_stream_wait_value32(edge, ctypes.c_void_p(self.flags.ptr + 4), number - 1))
                 if up:
-                    runtime.check(library.sc_stream_wait_value32(stream, ctypes.c_void_p(self.flags.ptr), number - 1))
+                    # my first h real planes become the upper neighbour's lower ghost planes
+                    shift = slab.counts[slab.rank - 1] * plane
+                    self.concrete.launch([current] + tables, target, top[0], top[1], edge,
+                                         peer_pointer=up["buffers"][target_index], peer_shift=shift)
                 if down:
-                    runtime.check(library.sc_stream_wait_value32(stream, ctypes.c_void_p(self.flags.ptr + 4), number - 1))
-            if up:
-                # my first h real planes become the upper neighbour's lower ghost planes
-                shift = slab.counts[slab.rank - 1] * plane
-                self.concrete.launch([current] + tables, target, top[0], top[1], stream,
-                                     peer_pointer=up["buffers"][target_index], peer_shift=shift)
-            if down:
-                shift = -slab.planes * plane
-                self.concrete.launch([current] + tables, target, bottom[0], bottom[1], stream,
-                                     peer_pointer=down["buffers"][target_index], peer_shift=shift)
-            if up or down:
+                    shift = -slab.planes * plane
+                    self.concrete.launch([current] + tables, target, bottom[0], bottom[1], edge,
+                                         peer_pointer=down["buffers"][target_index], peer_shift=shift)
                 runtime.launch(self.device.utils(), "sc_signal", signal_geometry,
                                [ctypes.c_void_p(up["flags"] + 4 if up else 0),
                                 ctypes.c_void_p(down["flags"] if down else 0),
-                                ctypes.c_uint32(number)], stream)
-            self.concrete.launch([current] + tables, target, interior[0], interior[1], stream)
+                                ctypes.c_uint32(number)], edge)
+                runtime.check(library.sc_event_record(self.edge_done, edge))
+            self.concrete.launch([current] + tables, target, interior[0], interior[1], main)
+            if exchanging:
+                runtime.check(library.sc_event_record(self.interior_done, main))
+                self._events_armed = True
             self.sweep += 1
+
+    def join(self):
+        """Make the main stream wait for the edge stream's last sweep (for timing with events
+        recorded on the main stream)."""
+        if self._events_armed:
+            self.runtime.check(self.library.sc_stream_wait_event(self.device.stream, self.edge_done))
 
     def synchronize(self):
         self.device.synchronize(self.device.stream)
+        self.device.synchronize(self.edge_stream)

@@ -34,6 +34,7 @@ def run(args, workload):
     with bench_module.ClockSampler(local_rank) as clocks:
         runtime.check(library.sc_event_record(start, device.stream))
         slab.iterate(args.steps)
+        slab.join()
         runtime.check(library.sc_event_record(stop, device.stream))
         slab.synchronize()
     dist.barrier()
@@ -91,7 +92,7 @@ def run(args, workload):
                        "ghost planes written by the neighbour's kernel through NVLink peer memory".format(
                            decomposition.planes),
                        "strategy": plan.strategy, "l2": "per-GPU slab in+out larger than L2",
-                       "kernel": plan.notes.get("config", {}), "launches_per_sweep": 4,
+                       "kernel": plan.notes.get("config", {}), "launches_per_sweep": 4, "streams": "boundary planes + signal on an edge stream, interior on the main stream",
                        "checksum": "{:016x}".format(checksum)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_source,
