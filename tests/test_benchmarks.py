@@ -1,0 +1,33 @@
+"""The reference-shaped benchmark harness."""
+import numpy
+import pytest
+
+from benchmarks.stencil_benchmarker import StencilBenchmarker, StencilTest, PrimedStencilTest
+from stencil_code_b200.library.jacobi_stencil import Jacobi
+
+
+class TinyBenchmarker(StencilBenchmarker):
+    def matrix_iterator(self):
+        for size in (6, 9):
+            yield numpy.random.random([size, size]).astype(numpy.float32)
+
+
+def test_harness_with_the_python_interpreter():
+    lines = []
+    rows = TinyBenchmarker([StencilTest("unprimed", stencil=Jacobi, backend='python'),
+                            PrimedStencilTest("primed", stencil=Jacobi, backend='python')],
+                           iterations=2).run(out=lines.append)
+    assert len(rows) == 4 and len(lines) == 4
+    assert rows[0][0] == (6, 6) and rows[0][1] == "unprimed" and rows[0][2] > 0
+    assert lines[0].startswith("(6, 6),unprimed,")
+    with pytest.raises(Exception):
+        StencilTest("x", Jacobi, 'python').average_time("missing")
+
+
+@pytest.mark.gpu
+def test_reference_benchmark_drivers_on_cuda():
+    from benchmarks import laplacian, convolve
+    rows = laplacian.main(iterations=1)
+    assert len(rows) == 3 * 2 * 2 and all(row[2] > 0 for row in rows)
+    results = convolve.main(sizes=(256, 1024), iterations=2, out=lambda line: None)
+    assert [r[0] for r in results] == [256, 1024]

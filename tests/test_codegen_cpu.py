@@ -130,3 +130,84 @@ def test_halo_slabs_cover_matches_enumerator():
     slabs = planner.halo_slabs((6, 7, 8), (1, 2, 1))
     count = sum((a1 - a0) * (b1 - b0) * (c1 - c0) for (a0, a1), (b0, b1), (c0, c1) in slabs)
     assert count == len(list(HaloEnumerator((1, 2, 1), (6, 7, 8)))) == 6 * 7 * 8 - 4 * 3 * 6
+
+
+# ---- large neighborhoods: tiled plane kernels with re-rolled neighbor loops ------------------------
+def bilateral_plan(shape=(256, 512), sigma_d=3):
+    from stencil_code_b200.library.better_bilateral_filter import BetterBilateralFilter
+    stencil = BetterBilateralFilter(sigma_d, 70)
+    return make_plan(stencil, [(shape, numpy.float32), (stencil.distance_lut.shape, numpy.float32),
+                               (stencil.intensity_lut.shape, numpy.float32)], 'stream')
+
+
+def test_bilateral_is_tiled_rolled_and_uses_the_fast_table_index():
+    plan = bilateral_plan()
+    config = plan.notes['config']
+    assert config['embedded_plane'] and config['mode'] == 'smem' and config['static_smem'] == 256 * 128
+    roll = codegen_stream.find_rolled_run(codegen_stream.embed_as_plane(plan.program))
+    assert roll is not None and len(roll['dys']) == 19 and len(roll['dxs']) == 19
+    assert roll['stop'] - roll['start'] == 361
+    kinds = [p[0] for p in roll['params'] if p is not None]
+    assert kinds == ['table']                       # filter_d[(int)distance] -> per-tap parameter
+    source = plan.source
+    assert "#pragma unroll 1" in source and "for (int tr_ = 0; tr_ < 19; ++tr_)" in source
+    assert "__fadd_rz(fabsf(" in source and "8388608.0f" in source      # abs((int)x) as FADD.RZ
+    assert "rep2[" in source and "<< 5) + lane]" in source               # bank-replicated LUT
+    assert len(source) < 80 * 1024                                       # 361 taps are NOT unrolled
+    assert runtime.compile_source(source, "bilateral.cu", plan.options).cubin()[:4] == b"\x7fELF"
+
+
+def test_rolled_loop_with_constant_coefficients():
+    from stencil_code_b200.library.convolution import ConvolutionFilter
+    kernel = numpy.arange(1, 82, dtype=numpy.float64).reshape(9, 9) / 7.0      # non-symmetric doubles
+    stencil = ConvolutionFilter(convolution_array=kernel, boundary_handling='clamp')
+    plan = make_plan(stencil, [((96, 256), numpy.float32), ((81,), numpy.float64)], 'stream')
+    lifted = codegen_stream.embed_as_plane(plan.program) if plan.notes['config']['embedded_plane'] else plan.program
+    roll = codegen_stream.find_rolled_run(lifted)
+    if plan.notes['config']['mode'] == 'smem':
+        assert roll is not None and [p[0] for p in roll['params'] if p is not None] == ['const']
+        assert "__constant__ double cpar" in plan.source
+    runtime.compile_source(plan.source, "conv9.cu", plan.options)
+
+
+def test_small_neighborhoods_are_not_rolled():
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    plan = make_plan(LaplacianKernel(), [((24, 40, 128), numpy.float32)], 'stream')
+    assert codegen_stream.find_rolled_run(plan.program) is None and "tr_" not in plan.source
+
+
+# ---- temporal blocking -----------------------------------------------------------------------------
+def test_temporal_blocking_eligibility_and_compile():
+    from stencil_code_b200.backend.cuda import codegen_temporal
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    from stencil_code_b200.library.laplacian_27pt import SpecializedLaplacian27
+    from stencil_code_b200.library.simple import SimpleKernel
+    shape = (64, 96, 512)
+    for mode in ('clamp', 'zero', 'copy'):
+        for stencil in (Jacobi3D(boundary_handling=mode), LaplacianKernel(boundary_handling=mode)):
+            plan = make_plan(stencil, [(shape, numpy.float32)], 'stream')
+            ok, why = codegen_temporal.eligible(plan.program, plan.domain)
+            assert ok, why
+            fused = codegen_temporal.make_plan(plan.program, plan.domain, planner.B200, plan.options)
+            assert fused.strategy == 'temporal' and "bar.sync 1" in fused.source
+            runtime.compile_source(fused.source, "temporal.cu", fused.options)
+            launch = fused.geometry(0, shape[0])
+            config = fused.notes['config']
+            assert launch.grid[0] * config['OUT_COLS'] >= shape[2] and launch.grid[1] * config['OUT_ROWS'] >= shape[1]
+    plan27 = make_plan(SpecializedLaplacian27(), [(shape, numpy.float32), ((4,), numpy.float32)], 'stream')
+    assert not codegen_temporal.eligible(plan27.program, plan27.domain)[0]       # corner taps at dz != 0
+    plan2d = make_plan(SimpleKernel(), [((2048, 2048), numpy.float32)], 'stream')
+    assert not codegen_temporal.eligible(plan2d.program, plan2d.domain)[0]
+    slab = make_plan(Jacobi3D(), [(shape, numpy.float32)], 'stream', open_faces=(True, False))
+    assert not codegen_temporal.eligible(slab.program, slab.domain)[0]
+
+
+def test_slab_domain_constants():
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    plan = make_plan(Jacobi3D(), [((34, 64, 256), numpy.float32)], 'stream', open_faces=(True, True))
+    domain = plan.domain
+    assert domain.sweep_range == (1, 33) and domain.clamp_lo[0] == 0 and domain.clamp_hi[0] == 33
+    top = make_plan(Jacobi3D(), [((34, 64, 256), numpy.float32)], 'stream', open_faces=(False, True)).domain
+    assert top.clamp_lo[0] == 1 and top.interior_lo[0] == 2 and top.interior_hi[0] == 34
+    assert "out_peer" in plan.source
