@@ -257,14 +257,20 @@ def choose_config(program, domain, device_props, override=None):
             candidates.append(dict(TX=128, TY=TY, BY=BY, NCW=NCW, U=1, prefetch=prefetch))
     else:
         # rank 2: every consumer warp owns a 128-column sub-tile with its own TMA box and halo
-        for NCW, U in ((4, 8), (8, 8), (4, 16), (2, 16), (2, 8), (1, 16), (1, 8)):
-            candidates.append(dict(TX=NCW * 128, TY=1, BY=1, NCW=NCW, U=U, prefetch=2))
+        # BY > 1: a thread owns BY four-column blocks, one in each of BY sub-tiles of its warp
+        # (halves the per-point cost of the row/stage bookkeeping, which bounds 5x5-like stencils)
+        # Listed in measured order (B200, conv 5x5 16384^2 clamp, GStencil/s): (4,4,2) 764,
+        # (4,4,1) 678, (4,8,1) 672, (2,8,2) 538, (4,8,2) 509; 3x3 8192^2: (4,4,2) 680, (4,8,1) 665.
+        # Among the candidates that waste the fewest lanes on the grid's width the first one wins.
+        for NCW, U, BY in ((4, 4, 2), (4, 8, 1), (4, 4, 1), (2, 8, 1), (2, 4, 1), (8, 8, 1), (4, 16, 1),
+                           (2, 16, 1), (1, 16, 1), (1, 8, 1), (1, 4, 1)):
+            candidates.append(dict(TX=NCW * BY * 128, TY=1, BY=BY, NCW=NCW, U=U, prefetch=2))
     best = None
     if any(k in override for k in ('TY', 'BY', 'NCW', 'U')):
         forced = dict(candidates[0])
         forced.update({k: v for k, v in override.items() if k in forced})
         if rank == 2:
-            forced['TX'] = forced['NCW'] * 128
+            forced['TX'] = forced['NCW'] * forced['BY'] * 128
         candidates = [forced]
     elif 'prefetch' in override:
         for cand in candidates:
@@ -289,7 +295,7 @@ def choose_config(program, domain, device_props, override=None):
         if pitch > 256:
             continue
         rows = (cand['TY'] + 2 * hy) if rank == 3 else U
-        n_sub = 1 if rank == 3 else cand['NCW']
+        n_sub = 1 if rank == 3 else cand['NCW'] * cand['BY']
         stage_floats = n_sub * rows * pitch
         stage_bytes = stage_floats * 4
         stage_bytes_aligned = (stage_bytes + 127) // 128 * 128
@@ -341,6 +347,9 @@ def choose_config(program, domain, device_props, override=None):
             # says (Laplacian 512^3: 690 vs 620 GStencil/s); with 128 tiles per plane
             # (256x1024x1024) the big tile wins (770 vs 679)
             score *= {1: 1.10, 2: 1.04}.get(blocks_per_sm, 1.0)
+        if rank == 2 and not any(k in override for k in ('TY', 'BY', 'NCW', 'U')):
+            few_warps = {1: 1.3, 2: 1.1}.get(cand['NCW'], 1.0)
+            score = waste * few_warps * 100 + 0.5 * candidates.index(cand)      # lane waste, then measured order
         if embedded:
             score = float(len(candidates) - candidates.index(cand)) * -1.0      # first that fits wins
         config = StreamConfig(rank=rank, PADX=PADX, HX=hx, HY=hy, HZ_LO=fp.hz_lo, HZ_HI=fp.hz_hi, W=W,
@@ -465,6 +474,13 @@ def generate(program, domain, cfg):
             return value_name(g, slot_of(phase, age, (g, row, col)), row, col)
         return value_name(g, "a" + tag(age), row, col)
 
+    # rank 2: a thread's block b lives in sub-tile (warp*BY + b): "row" stride = one sub-tile,
+    # and its columns start 128*b to the right of block 0
+    row_stride = PITCH if rank == 3 else SUBF
+
+    def col_base(b):
+        return "gx" if rank == 3 or b == 0 else "gx + {}".format(128 * b)
+
     roll = find_rolled_run(program) if (not regwin and rank == 3) else None
     if roll is not None and os.environ.get("STENCIL_CUDA_NO_ROLL"):
         roll = None
@@ -581,10 +597,14 @@ def generate(program, domain, cfg):
         e("const int gy = y0 + tr * {};".format(BY))
         e("const int sbase = ({} + tr * {}) * {} + {} + tq * 4;".format(HY, BY, PITCH, PADX))
     else:
-        e("const int tq = tid;                  // quad (4 columns) within the CTA's tile")
-        e("const int sbase = warp * {} + {} + lane * 4;   // own 128-column sub-tile".format(SUBF, PADX))
-    e("const int gx = x0 + tq * 4;          // first of this thread's 4 columns")
-    e("const bool col_ok = gx < {};".format(N2))
+        e("const int tq = warp * {} + lane;      // quad of block 0 within the CTA's tile".format(32 * BY))
+        e("const int sbase = warp * {} + {} + lane * 4;   // block 0's 128-column sub-tile".format(BY * SUBF, PADX))
+    e("const int gx = x0 + tq * 4;          // first of this thread's 4 columns (block 0)")
+    if rank == 3:
+        e("const bool col_ok = gx < {};".format(N2))
+    else:
+        for b in range(BY):
+            e("const bool col_ok{} = {} < {};".format(b, col_base(b), N2))
     clamp_rows = clamp and rank == 3 and (HY > 0 or BY > 1)
     clamp_cols = clamp and HX > 0
     if clamp_rows:
@@ -597,7 +617,8 @@ def generate(program, domain, cfg):
         if rank == 3:
             e("const bool x_edge = x0 == 0 || x0 + {} > {};".format(TX + HX, N2))
         else:
-            e("const bool x_edge = x0 + warp * 128 == 0 || x0 + warp * 128 + {} > {};".format(128 + HX, N2))
+            e("const bool x_edge = x0 + warp * {w} == 0 || x0 + warp * {w} + {r} > {n};".format(
+                w=128 * BY, r=128 * BY + HX, n=N2))
     if not clamp:
         e("u32 halo_mask = 0;                   // bit (b*4+j): the point lies in the in-plane halo")
         for b in range(BY):
@@ -609,9 +630,9 @@ def generate(program, domain, cfg):
                     if i_hi[1] < N1:
                         tests.append("gy + {} >= {}".format(b, i_hi[1]))
                 if i_lo[col_axis] > 0:
-                    tests.append("gx + {} < {}".format(j, i_lo[col_axis]))
+                    tests.append("{} + {} < {}".format(col_base(b), j, i_lo[col_axis]))
                 if i_hi[col_axis] < N2:
-                    tests.append("gx + {} >= {}".format(j, i_hi[col_axis]))
+                    tests.append("{} + {} >= {}".format(col_base(b), j, i_hi[col_axis]))
                 if tests:
                     e("if ({}) halo_mask |= {}u;".format(" || ".join(tests), 1 << (b * 4 + j)))
     for (arg, index), ctype in sorted(const_refs.items()):
@@ -627,14 +648,15 @@ def generate(program, domain, cfg):
 
     counter = [0]
 
-    def emit_column_fix(names_by_col):
+    def emit_column_fix(names_by_col, row=0):
         """cascade the nearest in-grid column outward (names_by_col: col -> register name)"""
+        base = col_base(row if rank == 2 else 0)
         left = sorted((c for c in names_by_col if c < 0), reverse=True)
         right = sorted(c for c in names_by_col if c > 3)
         for c in left:
-            e("if (gx + ({}) < 0) {} = {};".format(c, names_by_col[c], names_by_col[c + 1]))
+            e("if ({} + ({}) < 0) {} = {};".format(base, c, names_by_col[c], names_by_col[c + 1]))
         for c in right:
-            e("if (gx + {} > {}) {} = {};".format(c, N2 - 1, names_by_col[c], names_by_col[c - 1]))
+            e("if ({} + {} > {}) {} = {};".format(base, c, N2 - 1, names_by_col[c], names_by_col[c - 1]))
 
     def emit_loads(phase, g, age, keys):
         """shared memory -> registers for the (row, col) values `keys` of grid g at `age`"""
@@ -645,7 +667,7 @@ def generate(program, domain, cfg):
             by_row.setdefault(row, set()).add(col)
         for row in sorted(by_row):
             for first, width, used in _group_loads(by_row[row]):
-                offset = "{}".format(row * PITCH + first)
+                offset = "{}".format(row * row_stride + first)
                 if clamp_rows:
                     offset = "ro{} + ({})".format(tag(row), offset)
                 if width == 1:
@@ -668,7 +690,7 @@ def generate(program, domain, cfg):
                 if not outer:
                     continue
                 span = range(min(min(outer), 0), max(max(outer), 3) + 1)
-                emit_column_fix({c: name_of(phase, g, age, row, c) for c in span if (g, row, c) in fp.ages})
+                emit_column_fix({c: name_of(phase, g, age, row, c) for c in span if (g, row, c) in fp.ages}, row)
             e.close()
 
     current_tap_text, current_acc = [None], [None]
@@ -903,8 +925,8 @@ def generate(program, domain, cfg):
                 cond = "col_ok && gy + {} < row_end".format(b)
                 address = "out + ((i64)z * {} + (gy + {})) * {} + gx".format(N1, b, N2)
             else:
-                cond = "col_ok"
-                address = "out + (i64)z * {} + gx".format(N2)
+                cond = "col_ok{}".format(b)
+                address = "out + (i64)z * {} + {}".format(N2, col_base(b))
             e.open("if ({})".format(cond))
             e("float* const dst = {};".format(address))
             e("st_global_v4(dst, {});".format(", ".join(acc[b])))

@@ -133,6 +133,7 @@ class Module(object):
     def __init__(self, handle, name):
         self.handle = handle
         self.name = name
+        self.from_disk_cache = False
         self._keepalive = []
 
     def cubin(self):
@@ -160,14 +161,54 @@ class Module(object):
         return blocks.value
 
 
+def _cache_dir():
+    """Directory of the on-disk cubin cache (the counterpart of ctree's on-disk JIT cache, which
+    the reference relies on for its "without compile" timings); STENCIL_CUDA_CACHE=off disables."""
+    configured = os.environ.get("STENCIL_CUDA_CACHE")
+    if configured in ("off", "0"):
+        return None
+    path = configured or os.path.join(os.path.expanduser("~"), ".cache", "stencil_code_b200")
+    try:
+        os.makedirs(path, exist_ok=True)
+        return path
+    except OSError:
+        return None
+
+
 def compile_source(source, name="stencil_kernel.cu", options=()):
-    """NVRTC-compile CUDA C++ for sm_100a (works without a GPU; the shim caches by source)."""
+    """CUDA C++ -> sm_100a module.  Looks in the on-disk cubin cache first (keyed by source and
+    options), else compiles with NVRTC through the shim (works without a GPU) and stores the cubin."""
+    import hashlib
     library = load_library()
+    directory = _cache_dir()
+    cached_path = None
+    if directory is not None:
+        digest = hashlib.sha256(("\n".join(options) + "\0" + source).encode()).hexdigest()[:32]
+        cached_path = os.path.join(directory, "{}_{}.cubin".format(os.path.splitext(name)[0], digest))
+        if os.path.exists(cached_path):
+            try:
+                with open(cached_path, "rb") as handle:
+                    data = handle.read()
+                if data[:4] == b"\x7fELF":
+                    module = module_from_cubin(data, name)
+                    module.from_disk_cache = True
+                    return module
+            except (OSError, StencilException):
+                pass
     raw = (ctypes.c_char_p * len(options))(*[o.encode() for o in options])
     handle = ctypes.c_void_p()
     check(library.sc_compile(source.encode(), name.encode(), raw, len(options), ctypes.byref(handle)),
           "JIT compile of " + name)
-    return Module(handle, name)
+    module = Module(handle, name)
+    if cached_path is not None:
+        try:
+            temporary = cached_path + ".tmp{}".format(os.getpid())
+            with open(temporary, "wb") as out:
+                out.write(module.cubin())
+            os.replace(temporary, cached_path)
+        except OSError:
+            pass
+    return module
 
 
 def module_from_cubin(data, name="cubin"):

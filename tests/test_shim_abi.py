@@ -38,3 +38,16 @@ def test_nvrtc_compiles_sm100a_cubin_without_a_gpu():
                                     "tiny.cu", ("--fmad=false",))
     cubin = module.cubin()
     assert cubin[:4] == b"\x7fELF" and len(cubin) > 1000
+
+
+def test_on_disk_cubin_cache(tmp_path, monkeypatch):
+    monkeypatch.setenv("STENCIL_CUDA_CACHE", str(tmp_path))
+    source = 'extern "C" __global__ void cached_kernel(float* p) { p[threadIdx.x] = 3.0f; }'
+    first = runtime.compile_source(source, "cached.cu", ("--fmad=false",))
+    assert not first.from_disk_cache and len(list(tmp_path.glob("cached_*.cubin"))) == 1
+    second = runtime.compile_source(source, "cached.cu", ("--fmad=false",))
+    assert second.from_disk_cache and second.cubin() == first.cubin()
+    other = runtime.compile_source(source, "cached.cu", ("--fmad=true",))
+    assert not other.from_disk_cache
+    monkeypatch.setenv("STENCIL_CUDA_CACHE", "off")
+    assert not runtime.compile_source(source, "cached.cu", ("--fmad=false",)).from_disk_cache
