@@ -42,8 +42,8 @@ def eligible(program, domain):
         return False, "exactly one float32 grid argument"
     if program.shape[-1] % 4 or program.shape[-1] < 256 or program.shape[1] < 16 or program.shape[0] < 8:
         return False, "grid too small or rows not 16-byte multiples"
-    if domain.is_slab:
-        return False, "slab domains exchange ghost planes every sweep"
+    if domain.is_slab and domain.slab_ghost < 2 * program.ghost_depth[0]:
+        return False, "slab carries fewer than two ghost depths of planes"
     data_tables = table_plan(program, False)[0]
     if data_tables:
         return False, "data-indexed tables"
@@ -164,7 +164,7 @@ def generate(program, domain, cfg):
       "BY={} ring S={}".format(shape, boundary, MY, cfg.OUT_ROWS, cfg.OUT_COLS, BY, S))
     params = ["const {}* __restrict__ a{}".format(arg.ctype, arg.index) for arg in program.args]
     params += ["const __grid_constant__ TensorMap tm0", "float* __restrict__ out",
-               "int a0_begin", "int a0_end", "int chunk_len"]
+               "float* __restrict__ out_peer", "i64 peer_shift", "int a0_begin", "int a0_end", "int chunk_len"]
     e('extern "C" __global__ void __launch_bounds__({}, {})'.format(cfg.threads, cfg.blocks_per_sm))
     e("{}({})".format(FUNCTION, ", ".join(params)))
     e.open("")
@@ -422,8 +422,11 @@ def generate(program, domain, cfg):
         for b in range(BY):
             row_ok = "tr * {by} + {b} >= {hy} && tr * {by} + {b} < {hi} && gy + {b} >= 0 && gy + {b} < {n1}".format(
                 by=BY, b=b, hy=HY, hi=MY - HY, n1=N1)
-            e("if (col_ok && {}) st_global_v4(out + ((i64)zo * {} + (gy + {})) * {} + gx, {});".format(
-                row_ok, N1, b, N2, ", ".join(acc[b])))
+            e.open("if (col_ok && {})".format(row_ok))
+            e("float* const dst = out + ((i64)zo * {} + (gy + {})) * {} + gx;".format(N1, b, N2))
+            e("st_global_v4(dst, {});".format(", ".join(acc[b])))
+            e("if (out_peer) st_global_v4(out_peer + (dst - out) + peer_shift, {});".format(", ".join(acc[b])))
+            e.close()
         e.close()   # unit >= 4
         e.close()   # unit >= 2
         e("++unit;")

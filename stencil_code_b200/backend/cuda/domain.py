@@ -9,17 +9,20 @@ are compile-time constants of the generated kernel.
 
 
 class Domain(object):
-    def __init__(self, shape, ghost_depth, open_lo=False, open_hi=False):
+    def __init__(self, shape, ghost_depth, open_lo=False, open_hi=False, slab_ghost=None):
         """
         :param shape: shape of the LOCAL array (ghost planes included when a face is open)
         :param ghost_depth: per-dimension ghost depth of the stencil
         :param open_lo / open_hi: axis-0 faces that border another slab
+        :param slab_ghost: ghost planes per side of a slab (default: the stencil's axis-0 ghost
+            depth; twice that when pairs of sweeps are fused between exchanges)
         """
         self.shape = tuple(int(s) for s in shape)
         self.ghost = tuple(int(g) for g in ghost_depth)
         self.open_lo, self.open_hi = bool(open_lo), bool(open_hi)
         dim = len(self.shape)
-        h0 = self.ghost[0]
+        h0 = self.ghost[0] if slab_ghost is None else int(slab_ghost)
+        self.slab_ghost = h0
         # first / last index that holds real data of this rank's part of the global grid
         self.data_lo = [0] * dim
         self.data_hi = [n - 1 for n in self.shape]
@@ -52,4 +55,4 @@ class Domain(object):
         return self.data_lo[0], self.data_hi[0] + 1
 
     def key(self):
-        return (self.shape, self.ghost, self.open_lo, self.open_hi)
+        return (self.shape, self.ghost, self.open_lo, self.open_hi, self.slab_ghost)

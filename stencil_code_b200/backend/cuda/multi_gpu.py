@@ -30,18 +30,19 @@ from ...stencil_exception import StencilException
 class SlabDecomposition(object):
     """Pure host arithmetic of the axis-0 slab cut (unit-tested on CPU with gloo)."""
 
-    def __init__(self, global_shape, ghost0, world, rank):
+    def __init__(self, global_shape, ghost0, world, rank, ghost_planes=None):
         self.global_shape = tuple(int(s) for s in global_shape)
-        self.h = int(ghost0)
+        self.h = int(ghost0)                                    # the stencil's axis-0 ghost depth
+        self.g = self.h if ghost_planes is None else int(ghost_planes)   # ghost planes per slab side
         self.world, self.rank = int(world), int(rank)
         n0 = self.global_shape[0]
         if self.world < 1 or not (0 <= self.rank < self.world):
             raise StencilException("bad rank {} of {}".format(rank, world))
         base, extra = divmod(n0, self.world)
         counts = [base + (1 if r < extra else 0) for r in range(self.world)]
-        if min(counts) < max(1, 2 * self.h):
+        if min(counts) < max(1, 2 * self.g):
             raise StencilException("{} planes over {} ranks leaves slabs thinner than twice the "
-                                   "ghost depth {}".format(n0, world, self.h))
+                                   "{} ghost planes".format(n0, world, self.g))
         self.counts = counts
         self.starts = [sum(counts[:r]) for r in range(self.world)]
         self.start = self.starts[self.rank]
@@ -50,14 +51,14 @@ class SlabDecomposition(object):
         self.open_lo = self.world > 1 and self.rank > 0
         self.open_hi = self.world > 1 and self.rank < self.world - 1
         self.ghosted = self.world > 1
-        pad = 2 * self.h if self.ghosted else 0
+        pad = 2 * self.g if self.ghosted else 0
         self.local_shape = (self.planes + pad,) + self.global_shape[1:]
         self.plane_elems = int(numpy.prod(self.global_shape[1:], dtype=numpy.int64)) if len(self.global_shape) > 1 else 1
 
     @property
     def first_real(self):
         """local axis-0 index of this rank's first real plane"""
-        return self.h if self.ghosted else 0
+        return self.g if self.ghosted else 0
 
     def local_index(self, global_plane):
         return global_plane - self.start + self.first_real
@@ -66,8 +67,8 @@ class SlabDecomposition(object):
         """(top, interior, bottom) local axis-0 ranges of one sweep; top/bottom are the planes a
         neighbour needs (and the only ones that read ghost planes)."""
         lo, hi = self.first_real, self.first_real + self.planes
-        top = (lo, min(lo + self.h, hi)) if self.open_lo else (lo, lo)
-        bottom = (max(hi - self.h, top[1]), hi) if self.open_hi else (hi, hi)
+        top = (lo, min(lo + self.g, hi)) if self.open_lo else (lo, lo)
+        bottom = (max(hi - self.g, top[1]), hi) if self.open_hi else (hi, hi)
         return top, (top[1], bottom[0]), bottom
 
     def sends(self):
@@ -76,16 +77,17 @@ class SlabDecomposition(object):
         lo, hi = self.first_real, self.first_real + self.planes
         if self.open_lo:
             up_planes = self.counts[self.rank - 1]
-            plan.append((self.rank - 1, (lo, lo + self.h), (self.h + up_planes, 2 * self.h + up_planes)))
+            plan.append((self.rank - 1, (lo, lo + self.g), (self.g + up_planes, 2 * self.g + up_planes)))
         if self.open_hi:
-            plan.append((self.rank + 1, (hi - self.h, hi), (0, self.h)))
+            plan.append((self.rank + 1, (hi - self.g, hi), (0, self.g)))
         return plan
 
 
 class SlabStencil(object):
     """An iterated stencil on this rank's slab, exchanging ghost planes through peer memory."""
 
-    def __init__(self, stencil, global_shape, tables=(), world=None, rank=None, device_index=None):
+    def __init__(self, stencil, global_shape, tables=(), world=None, rank=None, device_index=None,
+                 allow_fused=True):
         import torch.distributed as dist
         from . import runtime
         self.dist = dist
@@ -94,17 +96,43 @@ class SlabStencil(object):
             world = dist.get_world_size() if dist.is_initialized() else 1
             rank = dist.get_rank() if dist.is_initialized() else 0
         self.stencil = stencil
-        self.slab = SlabDecomposition(global_shape, stencil.ghost_depth[0], world, rank)
         self.device = runtime.Device.get(device_index)
         self.library = runtime.load_library()
         self.tables = [numpy.ascontiguousarray(t) for t in tables]
-        slab = self.slab
+        h = stencil.ghost_depth[0]
 
         class _Shape(object):
             def __init__(self, shape, dtype):
                 self.shape, self.dtype = shape, numpy.dtype(dtype)
-        fake_args = (_Shape(slab.local_shape, numpy.float32),) + tuple(self.tables)
-        self.concrete = stencil.specializer.specialize(fake_args, open_faces=(slab.open_lo, slab.open_hi))
+
+        def specialise(slab):
+            fake_args = (_Shape(slab.local_shape, numpy.float32),) + tuple(self.tables)
+            return stencil.specializer.specialize(fake_args, open_faces=(slab.open_lo, slab.open_hi),
+                                                  slab_ghost=slab.g if slab.ghosted else None)
+        # Preferred layout: two ghost depths per side, so that pairs of sweeps run as one fused
+        # launch (codegen_temporal) between ghost exchanges.  Falls back to one ghost depth and
+        # single sweeps when the stencil is not eligible or the slabs are too thin.
+        self.slab, self.concrete, self.fused = None, None, None
+        if world > 1 and h > 0 and allow_fused:
+            try:
+                candidate = SlabDecomposition(global_shape, h, world, rank, ghost_planes=2 * h)
+                concrete = specialise(candidate)
+                if concrete.temporal() is not None:
+                    self.slab, self.concrete, self.fused = candidate, concrete, concrete.temporal()
+            except StencilException:
+                pass
+        if world > 1:
+            # every rank must take the same decision (it fixes the ghost layout)
+            votes = [None] * world
+            dist.all_gather_object(votes, self.fused is not None)
+            if not all(votes):
+                self.slab, self.concrete, self.fused = None, None, None
+        if self.slab is None:
+            self.slab = SlabDecomposition(global_shape, h, world, rank)
+            self.concrete = specialise(self.slab)
+            if world == 1 and allow_fused:
+                self.fused = self.concrete.temporal()
+        slab = self.slab
         self.nbytes = int(numpy.prod(slab.local_shape, dtype=numpy.int64)) * 4
         self.buffers = [self.device.alloc(self.nbytes), self.device.alloc(self.nbytes)]
         self.flags = self.device.alloc(256)
@@ -116,7 +144,8 @@ class SlabStencil(object):
                 ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(table.ctypes.data), table.nbytes, self.device.stream))
             self.table_buffers.append(buffer)
         self.device.synchronize()
-        self.sweep = 0
+        self.sweep = 0          # sweeps applied so far
+        self.step = 0           # launches-with-exchange so far (a fused step applies two sweeps)
         self.edge_stream = self.device._new_stream()
         self.edge_done = self.device.new_event()
         self.interior_done = self.device.new_event()
@@ -156,7 +185,7 @@ class SlabStencil(object):
 
     # -- data in / out ----------------------------------------------------------------------------
     def _current(self):
-        return self.buffers[self.sweep % 2]
+        return self.buffers[self.step % 2]
 
     def fill_uniform(self, seed=1, scale=1.0):
         """Counter-based uniform [0, scale) fill, a function of the GLOBAL element index, so every
@@ -178,7 +207,7 @@ class SlabStencil(object):
         self.synchronize()
         slab = self.slab
         lo = max(0, slab.start - slab.first_real)
-        hi = min(slab.global_shape[0], slab.stop + (slab.h if slab.ghosted else 0))
+        hi = min(slab.global_shape[0], slab.stop + (slab.g if slab.ghosted else 0))
         part = numpy.ascontiguousarray(global_grid[lo:hi], dtype=numpy.float32)
         local_lo = lo - (slab.start - slab.first_real)
         destination = self._current().ptr + local_lo * slab.plane_elems * 4
@@ -251,10 +280,21 @@ class SlabStencil(object):
         plane = slab.plane_elems
         signal_geometry = type("L", (), dict(grid=(1, 1, 1), block=(32, 1, 1), cluster=(1, 1, 1), smem=0))()
         exchanging = bool(up or down)
-        for _ in range(sweeps):
-            number = self.sweep + 1
-            current = self.buffers[self.sweep % 2].ptr
-            target_index = (self.sweep + 1) % 2
+        remaining = sweeps
+        while remaining > 0:
+            fused = self.fused is not None and remaining >= 2
+            applied = 2 if fused else 1
+
+            def run(begin, end, stream, peer_pointer=0, peer_shift=0):
+                if fused:
+                    self.concrete._launch_plan(self.fused[0], self.fused[1], [current] + tables, target,
+                                               begin, end, stream, peer_pointer, peer_shift)
+                else:
+                    self.concrete.launch([current] + tables, target, begin, end, stream,
+                                         peer_pointer=peer_pointer, peer_shift=peer_shift)
+            number = self.step + 1
+            current = self.buffers[self.step % 2].ptr
+            target_index = (self.step + 1) % 2
             target = self.buffers[target_index].ptr
             if exchanging:
                 if number > 1 or self._events_armed:
@@ -267,24 +307,22 @@ class SlabStencil(object):
                     if down:
                         runtime.check(library.sc_stream_wait_value32(edge, ctypes.c_void_p(self.flags.ptr + 4), number - 1))
                 if up:
-                    # my first h real planes become the upper neighbour's lower ghost planes
-                    shift = slab.counts[slab.rank - 1] * plane
-                    self.concrete.launch([current] + tables, target, top[0], top[1], edge,
-                                         peer_pointer=up["buffers"][target_index], peer_shift=shift)
+                    # my first g real planes become the upper neighbour's lower ghost planes
+                    run(top[0], top[1], edge, up["buffers"][target_index], slab.counts[slab.rank - 1] * plane)
                 if down:
-                    shift = -slab.planes * plane
-                    self.concrete.launch([current] + tables, target, bottom[0], bottom[1], edge,
-                                         peer_pointer=down["buffers"][target_index], peer_shift=shift)
+                    run(bottom[0], bottom[1], edge, down["buffers"][target_index], -slab.planes * plane)
                 runtime.launch(self.device.utils(), "sc_signal", signal_geometry,
                                [ctypes.c_void_p(up["flags"] + 4 if up else 0),
                                 ctypes.c_void_p(down["flags"] if down else 0),
                                 ctypes.c_uint32(number)], edge)
                 runtime.check(library.sc_event_record(self.edge_done, edge))
-            self.concrete.launch([current] + tables, target, interior[0], interior[1], main)
+            run(interior[0], interior[1], main)
             if exchanging:
                 runtime.check(library.sc_event_record(self.interior_done, main))
                 self._events_armed = True
-            self.sweep += 1
+            self.step += 1
+            self.sweep += applied
+            remaining -= applied
 
     def join(self):
         """Make the main stream wait for the edge stream's last sweep (for timing with events

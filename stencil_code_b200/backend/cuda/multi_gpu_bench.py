@@ -49,7 +49,7 @@ def run(args, workload):
     # end to end, one sweep per step: pinned host slab -> device, sweep, result -> pinned host
     decomposition = slab.slab
     lo = max(0, decomposition.start - decomposition.first_real)
-    hi = min(shape[0], decomposition.stop + decomposition.h)
+    hi = min(shape[0], decomposition.stop + decomposition.g)
     host_part = device.pinned_empty((hi - lo,) + tuple(shape[1:]), numpy.float32)
     host_part[...] = 0.5
     e2e_steps = 3
@@ -91,7 +91,9 @@ def run(args, workload):
             "config": {"workload": workload["label"] + ", slab-decomposed along axis 0, {} planes per GPU, "
                        "ghost planes written by the neighbour's kernel through NVLink peer memory".format(
                            decomposition.planes),
-                       "strategy": plan.strategy, "l2": "per-GPU slab in+out larger than L2",
+                       "sweeps_per_exchange": 2 if slab.fused is not None else 1,
+                       "ghost_planes_per_side": decomposition.g,
+                       "strategy": ("temporal2 (two sweeps fused per HBM pass and per ghost exchange)" if slab.fused is not None else plan.strategy), "l2": "per-GPU slab in+out larger than L2",
                        "kernel": plan.notes.get("config", {}), "launches_per_sweep": 4, "streams": "boundary planes + signal on an edge stream, interior on the main stream",
                        "checksum": "{:016x}".format(checksum)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -101,7 +103,7 @@ def run(args, workload):
                     "h2d_bytes_per_step": int(host_part.nbytes) * world,
                     "d2h_bytes_per_step": int(result.nbytes) * world,
                     "what": "per step: pinned host slab -> device, one sweep, slab -> pinned host, all ranks"},
-            "gpu_launches": args.steps * 4 * world,
+            "gpu_launches": (args.steps // 2 + args.steps % 2 if slab.fused is not None else args.steps) * 4 * world,
             "clocks": clocks.summary(),
         }
     slab.close()

@@ -466,9 +466,8 @@ class ConcreteCudaStencil(object):
             for spec in plan.tensor_maps:
                 values.append(self._tensor_map(spec, arg_pointers[spec.arg]))
             values.append(ctypes.c_void_p(out_pointer))
-            if plan.strategy != 'temporal':
-                values.append(ctypes.c_void_p(peer_pointer))
-                values.append(ctypes.c_longlong(peer_shift))
+            values.append(ctypes.c_void_p(peer_pointer))
+            values.append(ctypes.c_longlong(peer_shift))
             values.append(ctypes.c_int(a0_begin))
             values.append(ctypes.c_int(a0_end))
             geometry = plan.geometry(a0_begin, a0_end)

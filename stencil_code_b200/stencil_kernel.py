@@ -77,12 +77,12 @@ class SpecializedStencil(object):
         self.args = args
         return tuple(self._describe(arg) for arg in args)
 
-    def transform(self, arg_cfg, open_faces=(False, False)):
+    def transform(self, arg_cfg, open_faces=(False, False), slab_ghost=None):
         """Python AST -> semantic model -> CUDA plan (reference ``:278-344``).  ``open_faces``
         marks axis-0 faces that border another slab of a multi-GPU decomposition."""
         model = PythonToStencilModel().visit(self.original_tree)
         transformer = self.backend(self.args, None, self.kernel, arg_cfg=arg_cfg,
-                                   fusable_nodes=None, open_faces=open_faces)
+                                   fusable_nodes=None, open_faces=open_faces, slab_ghost=slab_ghost)
         return transformer.visit(model)
 
     def finalize(self, plan):
@@ -90,14 +90,14 @@ class SpecializedStencil(object):
         from .backend.cuda.runtime import ConcreteCudaStencil
         return ConcreteCudaStencil(plan)
 
-    def specialize(self, args, open_faces=(False, False)):
+    def specialize(self, args, open_faces=(False, False), slab_ghost=None):
         if len(args) == 0:
             raise StencilException("a stencil needs at least one input grid")
         arg_cfg = self.args_to_subconfig(args)
-        key = (arg_cfg, tuple(bool(f) for f in open_faces))
+        key = (arg_cfg, tuple(bool(f) for f in open_faces), slab_ghost)
         concrete = self._cache.get(key)
         if concrete is None:
-            concrete = self.finalize(self.transform(arg_cfg, open_faces))
+            concrete = self.finalize(self.transform(arg_cfg, open_faces, slab_ghost))
             self._cache[key] = concrete
         return concrete
 

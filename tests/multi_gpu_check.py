@@ -52,7 +52,8 @@ def main():
                 for _ in range(sweeps):
                     expected = reference_c(python_side, expected, *tables)
                 same = (combined.view(numpy.uint32) == expected.view(numpy.uint32)).all()
-                single = SlabStencil(make('cuda'), shape, tables=tables, world=1, rank=0, device_index=local_rank)
+                single = SlabStencil(make('cuda'), shape, tables=tables, world=1, rank=0, device_index=local_rank,
+                                     allow_fused=False)
                 single.load(grid)
                 single.iterate(sweeps)
                 single.synchronize()
@@ -63,17 +64,41 @@ def main():
                 failures += (not same) + (not same_sum)
             dist.barrier()
 
-    # 2. larger grid (stream strategy, many chunks), k GPUs vs 1 GPU by checksum
+    # 1b. a grid large enough for the fused two-sweep slab path (two ghost depths, one exchange
+    #     per pair of sweeps) against the CPU oracle, odd sweep count
+    shape, sweeps = (64, 128, 512), 5
+    grid = numpy.random.RandomState(8).random_sample(shape).astype(numpy.float32)
+    for mode in ("clamp", "copy"):
+        slab = SlabStencil(Jacobi3D(1.0, 0.25, boundary_handling=mode), shape, device_index=local_rank)
+        slab.load(grid)
+        slab.iterate(sweeps)
+        slab.synchronize()
+        parts = [None] * world
+        dist.all_gather_object(parts, numpy.array(slab.result()))
+        layout = "fused, {} ghost planes".format(slab.slab.g) if slab.fused is not None else "single sweeps"
+        slab.close()
+        if rank == 0:
+            expected = grid
+            python_side = Jacobi3D(1.0, 0.25, backend='python', boundary_handling=mode)
+            for _ in range(sweeps):
+                expected = reference_c(python_side, expected, variant='c_parallel')
+            same = (numpy.concatenate(parts, axis=0).view(numpy.uint32) == expected.view(numpy.uint32)).all()
+            print("oracle check Jacobi3D {} 64x128x512 x{} sweeps, {} ranks ({}): {}".format(
+                mode, sweeps, world, layout, "ok" if same else "MISMATCH"))
+            failures += not same
+        dist.barrier()
+
+    # 2. larger grid (stream strategy, many chunks), k GPUs vs 1 GPU (plain single sweeps) by checksum
     shape = (256, 256, 512)
     slab = SlabStencil(Jacobi3D(1.0, 0.25), shape, device_index=local_rank)
     slab.fill_uniform(seed=3)
     slab.iterate(25)
     slab.synchronize()
     total = slab.checksum()
-    strategy = slab.concrete.plan.strategy
+    strategy = "fused" if slab.fused is not None else slab.concrete.plan.strategy
     slab.close()
     if rank == 0:
-        single = SlabStencil(Jacobi3D(1.0, 0.25), shape, world=1, rank=0, device_index=local_rank)
+        single = SlabStencil(Jacobi3D(1.0, 0.25), shape, world=1, rank=0, device_index=local_rank, allow_fused=False)
         single.fill_uniform(seed=3)
         single.iterate(25)
         single.synchronize()

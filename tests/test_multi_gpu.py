@@ -26,6 +26,11 @@ def test_decomposition_arithmetic():
     assert single.local_shape == (50, 8, 8) and single.ranges() == ((0, 0), (0, 50), (50, 50))
     with pytest.raises(StencilException):
         SlabDecomposition((6, 8, 8), 2, 4, 0)
+    # two ghost depths per side: the layout of the fused two-sweep path
+    deep = SlabDecomposition((50, 8, 8), 1, 4, 1, ghost_planes=2)
+    assert deep.local_shape == (17, 8, 8) and deep.first_real == 2
+    assert deep.ranges() == ((2, 4), (4, 13), (13, 15))
+    assert deep.sends() == [(0, (2, 4), (15, 17)), (2, (13, 15), (0, 2))]
 
 
 WORKER = r'''
