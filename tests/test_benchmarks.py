@@ -31,3 +31,23 @@ def test_reference_benchmark_drivers_on_cuda():
     assert len(rows) == 3 * 2 * 2 and all(row[2] > 0 for row in rows)
     results = convolve.main(sizes=(256, 1024), iterations=2, out=lambda line: None)
     assert [r[0] for r in results] == [256, 1024]
+
+
+def test_demo_helpers():
+    from demo.bilateral_filter import synthetic_image, rescale_to_intensity
+    image = synthetic_image(64, 48)
+    assert image.shape == (48, 64) and image.dtype == numpy.uint8
+    scaled = rescale_to_intensity(image.astype(numpy.float32) * 0.01, float(image.mean()))
+    assert scaled.dtype == numpy.uint8 and abs(float(scaled.mean()) - float(image.mean())) < 1.5
+
+
+@pytest.mark.gpu
+def test_demo_on_cuda_matches_oracle():
+    from demo.bilateral_filter import synthetic_image, run
+    from cases import oracle_output
+    from stencil_code_b200.library.better_bilateral_filter import BetterBilateralFilter
+    image = synthetic_image(128, 96)
+    result, _ = run(image)
+    expected = oracle_output(BetterBilateralFilter(3, 70, backend='python'), image.astype(numpy.float32))
+    from demo.bilateral_filter import rescale_to_intensity
+    numpy.testing.assert_array_equal(result, rescale_to_intensity(expected, float(image.mean())))
