@@ -256,6 +256,14 @@ def other_workloads(peak):
             result = device_sweeps(make_workload(name, boundary, "cuda"), steps, 3, iterated)
             rows[label] = {"gstencil_s": round(result["gstencil_s"], 1), "ms_per_sweep": round(result["ms_per_sweep"], 4),
                            "frac_of_hbm_peak": round(result["gb_s"] / peak, 3), "strategy": result["strategy"]}
+            if name == "bilateral":
+                # not HBM bound: 361 taps/point at 7 instructions per tap (FSUB, FADD.RZ, LEA, LDS,
+                # FMUL, FMUL, FADD) against the FP32 issue rate of 148 SMs x 128 lanes x 1.965 GHz
+                taps = 361.0 * result["gstencil_s"] * 1e9
+                peak_taps = 148 * 128 * 1.965e9 / 7.0
+                rows[label]["instruction_roofline"] = {
+                    "bound": "fp32 issue", "instr_per_tap": 7, "achieved_taps_per_s": taps,
+                    "peak_taps_per_s": peak_taps, "frac": round(taps / peak_taps, 3)}
         except Exception as error:       # a failing extra must not lose the headline line
             rows[label] = {"error": str(error)[:200]}
     return rows

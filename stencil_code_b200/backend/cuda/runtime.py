@@ -411,7 +411,7 @@ class ConcreteCudaStencil(object):
         self._launches = {}
         self._temporal = None
         self._sc_launch = load_library().sc_launch
-        self.last_kernel_ms = None
+        self.last_duration = None        # seconds of the last call when STENCIL_CUDA_TIMING=1
 
     # -- argument checks (the reference's ndpointer argtypes raise TypeError on mismatch)
     def _check_args(self, args):
@@ -493,9 +493,19 @@ class ConcreteCudaStencil(object):
         if kwargs:
             raise StencilException("unexpected keyword arguments {}".format(sorted(kwargs)))
         self._check_args(args)
-        if _is_torch_tensor(args[0]):
-            return self._call_torch(args, out)
-        return self._call_numpy(args, out)
+        timed = os.environ.get("STENCIL_CUDA_TIMING", "0") not in ("0", "")
+        if timed:
+            # the reference's generated code reports its own run time through a `duration`
+            # out-parameter (backend/c.py:32-39); the analogue here is wall time of the call,
+            # device-synchronised, kept on the callable
+            import time
+            self.device.synchronize()
+            begin = time.perf_counter()
+        result = self._call_torch(args, out) if _is_torch_tensor(args[0]) else self._call_numpy(args, out)
+        if timed:
+            self.device.synchronize()
+            self.last_duration = time.perf_counter() - begin
+        return result
 
     def _call_torch(self, args, out):
         import torch
