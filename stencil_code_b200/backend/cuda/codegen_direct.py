@@ -94,12 +94,13 @@ def generate(program, domain):
             halo_value = "a0[idx]" if program.boundary == 'copy' else ctype_zero(program.out_ctype)
             if program.boundary == 'copy' and program.args[0].ctype != program.out_ctype:
                 halo_value = "({}){}".format(program.out_ctype, halo_value)
-            lines.append("    if ({}) {{ out[idx] = {}; if (out_peer) out_peer[idx + peer_shift] = {}; return; }}".format(
-                " || ".join(tests), halo_value, halo_value))
+            mirror = " if (out_peer) out_peer[idx + peer_shift] = {};".format(halo_value) if domain.is_slab else ""
+            lines.append("    if ({}) {{ out[idx] = {};{} return; }}".format(" || ".join(tests), halo_value, mirror))
     lines.append("    {} acc = {};".format(program.out_ctype, ctype_zero(program.out_ctype)))
     lines.extend(emit_statements(program, tap_text, table_text))
     lines.append("    out[idx] = acc;")
-    lines.append("    if (out_peer) out_peer[idx + peer_shift] = acc;")
+    if domain.is_slab:
+        lines.append("    if (out_peer) out_peer[idx + peer_shift] = acc;")
     lines.append("}")
     return "\n".join(lines) + "\n"
 

@@ -252,8 +252,12 @@ def choose_config(program, domain, device_props, override=None):
         for TY, BY, NCW in ((16, 2, 8), (32, 4, 8), (32, 2, 16), (16, 4, 4), (8, 1, 8)):
             candidates.append(dict(TX=128, TY=TY, BY=BY, NCW=NCW, U=1, prefetch=0))
     elif rank == 3:
-        for TY, BY, NCW, prefetch in ((64, 4, 16, 3), (32, 4, 8, 2), (32, 4, 8, 3), (16, 4, 4, 3),
-                                      (32, 2, 16, 3), (16, 2, 8, 3), (8, 2, 4, 3), (8, 1, 8, 3)):
+        # measured on B200 (GStencil/s; Laplacian 512^3 / Jacobi 2048x1024^2 / 256x1024^2 slab):
+        # (64,4,16,p2) 765 / 775 / 784, (64,4,16,p3) 729 / 766 / 768, (32,4,8,p3) 731 / 731 / 770,
+        # (32,4,8,p2) 700 / 671 / 681, (16,4,4,p3) 719 / 708 / 759.  Ties in the traffic model go
+        # to the earlier candidate.
+        for TY, BY, NCW, prefetch in ((64, 4, 16, 2), (64, 4, 16, 3), (32, 4, 8, 3), (32, 4, 8, 2), (16, 4, 4, 3),
+                                      (16, 2, 8, 3), (8, 2, 4, 3), (8, 1, 8, 3)):
             candidates.append(dict(TX=128, TY=TY, BY=BY, NCW=NCW, U=1, prefetch=prefetch))
     else:
         # rank 2: every consumer warp owns a 128-column sub-tile with its own TMA box and halo
@@ -339,14 +343,7 @@ def choose_config(program, domain, device_props, override=None):
         items = tiles * (-(-n_stream // chunk_len))
         fill = items / float(-(-items // slots) * slots)
         resident_warps = blocks_per_sm * cand['NCW']
-        score = waste * (1.0 + read_factor) / 2.0 / (fill ** 0.5) * (1.0 if resident_warps >= 12 else 1.1)
-        if tiles < slots / 2:
-            # measured on B200: when a plane has far fewer tiles than there are resident CTA slots
-            # (512^2 planes: 32 tiles of 64x128 for 148 slots) the sweep needs many axis-0 chunks
-            # per tile and runs 5-10 % faster with more, smaller CTAs per SM than the traffic model
-            # says (Laplacian 512^3: 690 vs 620 GStencil/s); with 128 tiles per plane
-            # (256x1024x1024) the big tile wins (770 vs 679)
-            score *= {1: 1.10, 2: 1.04}.get(blocks_per_sm, 1.0)
+        score = waste * (1.0 + read_factor) / 2.0 / (fill ** 0.25) * (1.0 if resident_warps >= 12 else 1.1)
         if rank == 2 and not any(k in override for k in ('TY', 'BY', 'NCW', 'U')):
             few_warps = {1: 1.3, 2: 1.1}.get(cand['NCW'], 1.0)
             score = waste * few_warps * 100 + 0.5 * candidates.index(cand)      # lane waste, then measured order
@@ -930,7 +927,8 @@ def generate(program, domain, cfg):
             e.open("if ({})".format(cond))
             e("float* const dst = {};".format(address))
             e("st_global_v4(dst, {});".format(", ".join(acc[b])))
-            e("if (out_peer) st_global_v4(out_peer + (dst - out) + peer_shift, {});".format(", ".join(acc[b])))
+            if domain.is_slab:          # only slabs mirror boundary planes into a neighbour's ghost planes
+                e("if (out_peer) st_global_v4(out_peer + (dst - out) + peer_shift, {});".format(", ".join(acc[b])))
             e.close()
         e.close()   # if unit >= W-1
         if not regwin:

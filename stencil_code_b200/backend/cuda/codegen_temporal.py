@@ -425,7 +425,8 @@ def generate(program, domain, cfg):
             e.open("if (col_ok && {})".format(row_ok))
             e("float* const dst = out + ((i64)zo * {} + (gy + {})) * {} + gx;".format(N1, b, N2))
             e("st_global_v4(dst, {});".format(", ".join(acc[b])))
-            e("if (out_peer) st_global_v4(out_peer + (dst - out) + peer_shift, {});".format(", ".join(acc[b])))
+            if domain.is_slab:          # only slabs mirror boundary planes into a neighbour's ghost planes
+                e("if (out_peer) st_global_v4(out_peer + (dst - out) + peer_shift, {});".format(", ".join(acc[b])))
             e.close()
         e.close()   # unit >= 4
         e.close()   # unit >= 2

@@ -210,4 +210,6 @@ def test_slab_domain_constants():
     assert domain.sweep_range == (1, 33) and domain.clamp_lo[0] == 0 and domain.clamp_hi[0] == 33
     top = make_plan(Jacobi3D(), [((34, 64, 256), numpy.float32)], 'stream', open_faces=(False, True)).domain
     assert top.clamp_lo[0] == 1 and top.interior_lo[0] == 2 and top.interior_hi[0] == 34
-    assert "out_peer" in plan.source
+    assert "if (out_peer)" in plan.source
+    single = make_plan(Jacobi3D(), [((34, 64, 256), numpy.float32)], 'stream')
+    assert "if (out_peer)" not in single.source        # the mirror store exists only in slab kernels

@@ -1,8 +1,3 @@
-P="python tools/probe.py"
-STENCIL_CUDA_STREAM="NCW=4,U=4,BY=2" $P simple1024 clamp 50 8192x8192
-STENCIL_CUDA_STREAM="NCW=4,U=4,BY=1" $P simple1024 clamp 50 8192x8192
-STENCIL_CUDA_STREAM="NCW=4,U=4,BY=2" $P simple1024 clamp 50 4096x4096
-STENCIL_CUDA_STREAM="NCW=4,U=4,BY=2" $P conv5 zero 10
-STENCIL_CUDA_STREAM="NCW=4,U=4,BY=2,prefetch=3" $P conv5 clamp 10
-STENCIL_CUDA_STREAM="NCW=8,U=4,BY=2" $P conv5 clamp 10
-STENCIL_CUDA_STREAM="NCW=4,U=4,BY=1" $P conv5 clamp 10
+python tools/probe_iter.py 2048x1024x1024 20
+python tools/probe.py jacobi3d clamp 6
+python tools/probe.py laplacian512 clamp 20
