@@ -124,7 +124,10 @@ def choose_config(program, device_props):
     return best
 
 
-def generate(program, domain, cfg):
+def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True):
+    """CUDA source of the fused kernel.  ``mirror``: also store results through ``out_peer`` (slab
+    boundary launches); defaults to ``domain.is_slab``."""
+    mirror = domain.is_slab if mirror is None else mirror
     shape = program.shape
     N0, N1, N2 = shape
     MY, BY, NCW, S = cfg.MY, cfg.BY, cfg.NCW, cfg.S
@@ -158,15 +161,16 @@ def generate(program, domain, cfg):
         return "tc{}_{}".format(ref.arg, _const_index(ref.index))
 
     e = _Emitter()
-    e.lines.append(PROLOGUE)
-    e.lines.append(PTX_HELPERS.replace("@STOP@", os.environ.get("STENCIL_CUDA_STORE_OP", ".cs")))
+    if prologue:
+        e.lines.append(PROLOGUE)
+        e.lines.append(PTX_HELPERS.replace("@STOP@", os.environ.get("STENCIL_CUDA_STORE_OP", ".cs")))
     e("// temporal strategy: two fused sweeps | grid {} boundary {} | mid tile {}x128, output {}x{}, "
       "BY={} ring S={}".format(shape, boundary, MY, cfg.OUT_ROWS, cfg.OUT_COLS, BY, S))
     params = ["const {}* __restrict__ a{}".format(arg.ctype, arg.index) for arg in program.args]
     params += ["const __grid_constant__ TensorMap tm0", "float* __restrict__ out",
                "float* __restrict__ out_peer", "i64 peer_shift", "int a0_begin", "int a0_end", "int chunk_len"]
     e('extern "C" __global__ void __launch_bounds__({}, {})'.format(cfg.threads, cfg.blocks_per_sm))
-    e("{}({})".format(FUNCTION, ", ".join(params)))
+    e("{}({})".format(function, ", ".join(params)))
     e.open("")
     e("extern __shared__ __align__(128) unsigned char smem_raw[];")
     e("float* const ring = reinterpret_cast<float*>(smem_raw);")
@@ -425,7 +429,7 @@ def generate(program, domain, cfg):
             e.open("if (col_ok && {})".format(row_ok))
             e("float* const dst = out + ((i64)zo * {} + (gy + {})) * {} + gx;".format(N1, b, N2))
             e("st_global_v4(dst, {});".format(", ".join(acc[b])))
-            if domain.is_slab:          # only slabs mirror boundary planes into a neighbour's ghost planes
+            if mirror:                  # slab boundary launches also fill the neighbour's ghost planes
                 e("if (out_peer) st_global_v4(out_peer + (dst - out) + peer_shift, {});".format(", ".join(acc[b])))
             e.close()
         e.close()   # unit >= 4
@@ -446,6 +450,10 @@ def make_plan(program, domain, device_props, options):
         raise StencilException("temporal blocking not applicable: " + why)
     cfg = choose_config(program, device_props)
     source = generate(program, domain, cfg)
+    if domain.is_slab:
+        # interior launches of a slab never mirror: a second entry point without that code
+        # (the kernel is issue bound; the unused mirror stores cost about 6 %)
+        source += generate(program, domain, cfg, function=FUNCTION + "_interior", mirror=False, prologue=False)
     n0, n1, n2 = program.shape
     specs = [TensorMapSpec(0, (n2, n1, n0), (n2 * 4, n1 * n2 * 4), (cfg.PITCH, cfg.ROWS, 1), tag="temporal")]
     tiles_x = -(-n2 // cfg.OUT_COLS)
@@ -461,5 +469,7 @@ def make_plan(program, domain, device_props, options):
         launch.extra = (chunk_len,)
         return launch
 
-    return CudaPlan(program, domain, 'temporal', source, FUNCTION, options, geometry,
+    plan = CudaPlan(program, domain, 'temporal', source, FUNCTION, options, geometry,
                     tensor_maps=specs, notes={'config': cfg.describe()})
+    plan.function_no_peer = FUNCTION + "_interior" if domain.is_slab else None
+    return plan

@@ -475,9 +475,12 @@ class ConcreteCudaStencil(object):
                 values.append(ctypes.c_int(extra))
             pointers = (ctypes.c_void_p * len(values))(
                 *[ctypes.cast(ctypes.byref(v), ctypes.c_void_p) for v in values])
+            function = plan.function
+            if not peer_pointer and getattr(plan, 'function_no_peer', None):
+                function = plan.function_no_peer
             prepared = (values, pointers, (ctypes.c_uint32 * 3)(*geometry.grid),
                         (ctypes.c_uint32 * 3)(*geometry.block), (ctypes.c_uint32 * 3)(*geometry.cluster),
-                        geometry.smem, plan.function.encode())
+                        geometry.smem, function.encode())
             if len(self._launches) > 256:
                 self._launches.clear()
             self._launches[key] = prepared
