@@ -98,7 +98,8 @@ def choose_config(program, device_props):
         rows = MY + 2 * hy
         stage_floats = (rows * pitch * 4 + 127) // 128 * 32
         mid_floats = MY * 128
-        smem = S * stage_floats * 4 + (3 * mid_floats + 2 * 128) * 4 + 2 * S * 8 + 128
+        pad_floats = max(1, hy) * 128                 # rows read above / below the mid buffers
+        smem = S * stage_floats * 4 + (3 * mid_floats + 2 * pad_floats) * 4 + 2 * S * 8 + 128
         threads = (NCW + 1) * 32
         if smem > device_props.smem_per_block_optin:
             continue
@@ -113,6 +114,7 @@ def choose_config(program, device_props):
         score = traffic * (1.0 + 0.15 * (redundancy - 1.0)) * (1.0 if blocks * NCW >= 16 else 1.08)
         config = TemporalConfig(MY=MY, BY=BY, NCW=NCW, S=S, HX=hx, HY=hy, PADX=PADX, PITCH=pitch, ROWS=rows,
                                 STAGE_FLOATS=stage_floats, STAGE_BYTES=rows * pitch * 4, MID_FLOATS=mid_floats,
+                                PAD_FLOATS=pad_floats,
                                 OUT_ROWS=out_rows, OUT_COLS=out_cols, smem_bytes=smem, threads=threads,
                                 blocks_per_sm=blocks, score=score)
         if best is None:
@@ -174,8 +176,9 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     e.open("")
     e("extern __shared__ __align__(128) unsigned char smem_raw[];")
     e("float* const ring = reinterpret_cast<float*>(smem_raw);")
-    e("float* const mid = ring + {} + 128;        // three mid buffers, one pad row on either side".format(S * SF))
-    e("u64* const bar_full = reinterpret_cast<u64*>(smem_raw + {});".format((S * SF + 3 * MF + 2 * 128) * 4))
+    e("float* const mid = ring + {} + {};        // three mid buffers, hy pad rows on either side".format(
+        S * SF, cfg.PAD_FLOATS))
+    e("u64* const bar_full = reinterpret_cast<u64*>(smem_raw + {});".format((S * SF + 3 * MF + 2 * cfg.PAD_FLOATS) * 4))
     e("u64* const bar_empty = bar_full + {};".format(S))
     e("const int tid = threadIdx.x;")
     e("const int warp = tid >> 5;")
