@@ -150,8 +150,9 @@ class ClockSampler(object):
 
 
 # ---- CPU legs --------------------------------------------------------------------------------------------
-def cpu_reference_run(workload, steps, warmup):
-    """The restated reference OpenMP backend on this host's cores (oracle/, kind 'port')."""
+def cpu_reference_run(workload, steps, warmup, min_seconds=0.0):
+    """The restated reference OpenMP backend on this host's cores (oracle/, kind 'port').
+    Runs `steps` sweeps, and keeps sweeping until `min_seconds` of CPU work have been timed."""
     from oracle.cref import ReferenceC, reference_args
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
@@ -164,15 +165,16 @@ def cpu_reference_run(workload, steps, warmup):
     for _ in range(max(1, warmup)):
         compiled(*args)
     times = []
-    for _ in range(steps):
+    while len(times) < steps or (sum(times) < min_seconds and len(times) < 2000):
         compiled(*args)
         times.append(compiled.last_seconds)
     seconds = sum(times) / len(times)
     points = float(numpy.prod(shape))
     return {"value": points / seconds / 1e9, "unit": "GStencil/s", "cores": cores, "kind": "port",
             "variant": variant,
-            "sample": "{} sweeps of {} ({} backend restated from the reference, gcc -O2 -std=c99 -fopenmp, "
-                      "OMP_NUM_THREADS={})".format(steps, "x".join(map(str, shape)), variant, cores),
+            "sample": "{} sweeps of {} = {:.1f} s of CPU work ({} backend restated from the reference, "
+                      "gcc -O2 -std=c99 -fopenmp, OMP_NUM_THREADS={})".format(
+                          len(times), "x".join(map(str, shape)), sum(times), variant, cores),
             "ms_per_sweep": seconds * 1e3}
 
 
@@ -380,7 +382,7 @@ def run_single_gpu(args, workload):
         line["workloads"] = other_workloads(peak)
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_reference_run(make_workload(args.workload, args.boundary, "python"),
-                                                 steps=3, warmup=1)
+                                                 steps=3, warmup=1, min_seconds=10.0)
     return line
 
 
