@@ -104,7 +104,7 @@ class ClockSampler(object):
         try:
             self.process = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
             self.thread = threading.Thread(target=self._read)
             self.thread.daemon = True
@@ -389,7 +389,7 @@ def run_single_gpu(args, workload):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
-    parser.add_argument("--steps", type=int, default=20)
+    parser.add_argument("--steps", type=int, default=None)
     parser.add_argument("--warmup", type=int, default=5)
     parser.add_argument("--workload", default=None)
     parser.add_argument("--boundary", default=None)
@@ -401,6 +401,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     if args.workload is None:
         args.workload = "laplacian512" if args.gpus == 1 else "jacobi3d"
+    if args.steps is None:
+        # long enough for nvidia-smi to sample clocks inside the timed region (sub-millisecond sweeps)
+        args.steps = {"laplacian512": 400, "simple1024": 2000, "conv5": 200, "bilateral": 10,
+                      "jacobi3d": 40}.get(args.workload, 20)
 
     if args.impl == "reference":
         if rank != 0:
