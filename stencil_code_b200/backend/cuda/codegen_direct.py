@@ -10,7 +10,6 @@ Every output element in the requested axis-0 range is written exactly once, so t
 needs no zero-fill beforehand (the reference's ``zeros`` allocation, ``stencil_kernel.py:412-416``,
 is folded into the kernel: the accumulator starts at 0).
 """
-from .. import point_program as pp
 from .codegen_common import PROLOGUE, ctype_zero, emit_statements
 
 BLOCK_THREADS = 256

@@ -65,9 +65,6 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const TensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(tm) : "memory");
 }

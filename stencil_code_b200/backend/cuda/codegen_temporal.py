@@ -29,7 +29,7 @@ from ...stencil_exception import StencilException
 from .. import point_program as pp
 from .codegen_common import PROLOGUE, emit_statements
 from .codegen_stream import (PTX_HELPERS, TensorMapSpec, Footprint, _Emitter, _group_loads, _tap3,
-                             _grid_args, table_plan, plan_chunks, _const_index, _LOCAL_NAME)
+                             _grid_args, table_plan, plan_chunks, _const_index)
 
 FUNCTION = "stencil_temporal2"
 

@@ -21,9 +21,7 @@ import numbers
 import numpy
 
 from ..stencil_exception import StencilException
-from ..stencil_model import (
-    KernelFunction, InteriorPointsLoop, NeighborPointsLoop, GridElement, MathFunction,
-    Constant, SymbolRef, SelfAttribute, BinaryOp, UnaryOp, FunctionCall, Assign, AugAssign)
+from ..stencil_model import InteriorPointsLoop, GridElement, SymbolRef
 from . import point_program as pp
 
 

@@ -4,7 +4,7 @@ device (the reference tests its planner the same way, ``test/test_local_size_com
 import numpy
 import pytest
 
-from cases import CASES, CASE_MODE_PAIRS, PAIR_IDS
+from cases import CASE_MODE_PAIRS, PAIR_IDS
 from stencil_code_b200.backend import point_program as pp
 from stencil_code_b200.backend.cuda import runtime, planner, codegen_stream
 from stencil_code_b200.python_frontend import PythonToStencilModel

@@ -5,7 +5,6 @@ compared as uint32.  Float tolerance used anywhere in this file: none -- summati
 preserved and FMA contraction is off, so the north-star's "bit-exact" branch applies to every
 case here (the <= 4 ulp branch is not needed).
 """
-import glob
 import os
 
 import numpy

@@ -3,7 +3,6 @@ import os
 import subprocess
 import sys
 
-import numpy
 import pytest
 
 from stencil_code_b200.backend.cuda.multi_gpu import SlabDecomposition

@@ -14,7 +14,7 @@ import os
 import numpy
 import pytest
 
-from cases import CASES, CASE_MODE_PAIRS, PAIR_IDS, oracle_output
+from cases import CASES, CASE_MODE_PAIRS, oracle_output
 from stencil_code_b200.library.diagnostic_stencil import DiagnosticStencil
 from stencil_code_b200.library.laplacian import LaplacianKernel
 
