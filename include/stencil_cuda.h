@@ -117,6 +117,19 @@ int         sc_launch(sc_module* module, const char* function,
                       const uint32_t grid[3], const uint32_t block[3], const uint32_t cluster[3],
                       uint32_t dynamic_smem, void* stream, void** args);
 
+/* `count` launches of one kernel alternating between two argument blocks (iterated sweeps that
+ * ping-pong between two buffers: even launches read A and write B, odd ones the reverse), enqueued
+ * from C so that short kernels are not bound by the caller's per-launch overhead.  Replaces the
+ * Python-level `g = stencil(g)` loop the reference's users write (examples/jacobi_3d.py).
+ * See SC_LAUNCH_PROGRAMMATIC below for `flags`.                                                  */
+int         sc_launch_pingpong(sc_module* module, const char* function,
+                               const uint32_t grid[3], const uint32_t block[3], uint32_t dynamic_smem,
+                               void* stream, void** args_even, void** args_odd, int count,
+                               uint32_t flags);
+/* flags: launch with programmatic stream serialization -- only for kernels that execute
+ * griddepcontrol.wait before they touch memory the preceding launch writes or reads            */
+#define SC_LAUNCH_PROGRAMMATIC 1u
+
 /* ---- streams and events --------------------------------------------------------------------- */
 int         sc_stream_create(void** stream);
 int         sc_stream_destroy(void* stream);

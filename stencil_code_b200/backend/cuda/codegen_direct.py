@@ -66,6 +66,8 @@ def generate(program, domain):
     lines.append('extern "C" __global__ void __launch_bounds__({})'.format(BLOCK_THREADS))
     lines.append("stencil_direct({})".format(", ".join(params)))
     lines.append("{")
+    lines.append("    pdl_launch_dependents();")
+    lines.append("    pdl_wait();")
     lines.append("    const i64 t = (i64)blockIdx.x * {} + threadIdx.x;".format(BLOCK_THREADS))
     lines.append("    if (t >= (i64)(a0_end - a0_begin) * {}LL) return;".format(per0))
     if dim == 1:

@@ -130,9 +130,10 @@ def applicable(program, domain, device_props, forced=False):
         return False, "a single plane/row along the streaming axis"
     if program.npoints < 4096:
         return False, "tiny grid"
-    if program.npoints < (1 << 21) and not forced:
-        # measured on B200: a 1024^2 sweep takes 6 us with one thread per point and 12 us through
-        # the TMA pipeline (fill latency of a handful of CTAs); the grid is L2 resident either way
+    if program.npoints < (1 << 20) and not forced:
+        # measured on B200 (us per dependent sweep, floor 4.1): 512^2 and 64^3 take 4.1 with one
+        # thread per point and 4.1-6.2 through the TMA pipeline; from 1024^2 (5.1 vs 6.2) and
+        # 128^3 (6.2 vs 10.3) on the pipeline wins
         return False, "small grid ({} points): launch-latency bound, direct is faster".format(program.npoints)
     lo, hi = program.tap_extent()
     if max(-lo[-1], hi[-1]) > 12:
@@ -333,17 +334,32 @@ def choose_config(program, domain, device_props, override=None):
             waste *= tiles_y * cand['TY'] / float(n_rows)
             read_factor *= (cand['TY'] + 2 * hy) / float(cand['TY'])
         slots = device_props.sm_count * blocks_per_sm
-        min_chunk = max(4 * W, 16) if rank == 3 else max(4 * U, 64)
-        chunks = plan_chunks(n_stream, tiles, slots, W, min_chunk)
+        min_chunk = chunk_floors(rank, W, U, override)
+        chunks = plan_chunks_adaptive(n_stream, tiles, slots, W, min_chunk, device_props.sm_count)
         chunk_len = -(-n_stream // chunks)
         read_factor *= (chunk_len + W - 1) / float(chunk_len)
         items = tiles * (-(-n_stream // chunk_len))
-        fill = items / float(-(-items // slots) * slots)
+        if items >= slots:
+            fill = items / float(-(-items // slots) * slots)
+        else:
+            # a grid too small to fill the resident slots: what counts is that every SM has work
+            sms = device_props.sm_count
+            fill = items / float(-(-items // sms) * sms)
         resident_warps = blocks_per_sm * cand['NCW']
         score = waste * (1.0 + read_factor) / 2.0 / (fill ** 0.25) * (1.0 if resident_warps >= 12 else 1.1)
+        if fill < 0.8:
+            score *= (0.8 / fill) ** 0.75
+        if rank == 3 and chunk_len < 32:
+            # short chunks: the pipeline start-up (about two plane times) shows unless a second
+            # resident CTA covers it.  Measured at 256^3: (64,4,16) one CTA/SM 680 GStencil/s,
+            # (32,4,8) two CTAs/SM 746-764
+            score *= 1.0 + 2.0 / chunk_len / min(blocks_per_sm, 2)
         if rank == 2 and not any(k in override for k in ('TY', 'BY', 'NCW', 'U')):
             few_warps = {1: 1.3, 2: 1.1}.get(cand['NCW'], 1.0)
-            score = waste * few_warps * 100 + 0.5 * candidates.index(cand)      # lane waste, then measured order
+            # lane waste, then measured order; a candidate that leaves SMs without a CTA loses to
+            # one that does not (1024^2 Jacobi: (4,4,2) 128 CTAs 6.2 us, (4,4,1) 256 CTAs 5.1 us)
+            starved = 1.1 if items < device_props.sm_count else 1.0
+            score = waste * few_warps * starved * 100 + 0.5 * candidates.index(cand)
         if embedded:
             score = float(len(candidates) - candidates.index(cand)) * -1.0      # first that fits wins
         config = StreamConfig(rank=rank, PADX=PADX, HX=hx, HY=hy, HZ_LO=fp.hz_lo, HZ_HI=fp.hz_hi, W=W,
@@ -353,12 +369,33 @@ def choose_config(program, domain, device_props, override=None):
                               SUB_FLOATS=rows * pitch,
                               blocks_per_sm=blocks_per_sm, footprint=fp, n_grids=n_grids,
                               score=score, TX=cand['TX'], TY=cand['TY'], BY=cand['BY'], NCW=cand['NCW'],
-                              U=cand['U'])
+                              U=cand['U'], min_chunk=min_chunk)
         if best is None or score < best.score - 1e-9:
             best = config
     if best is None:
         raise StencilException("no streaming tile fits this stencil in shared memory")
     return best
+
+
+def chunk_floors(rank, window, units_per_stage, override=None):
+    """(usual, small-grid) lower bounds of the axis-0 chunk length.  Long chunks keep the re-read of
+    the window-1 start-up planes (rows) per chunk small, which matters when they come from DRAM;
+    a grid that cannot give every SM a CTA at that length is L2-resident, and there short chunks
+    win: measured on B200, Jacobi 128^3 16.8 -> 6.2 us/sweep, 1024^2 14.4 -> 5.1 us/sweep."""
+    forced = (override or {}).get('min_chunk')
+    if forced:
+        return forced, forced
+    if rank == 3:
+        return max(4 * window, 16), window + 1
+    return max(4 * units_per_stage, 64), 2 * units_per_stage
+
+
+def plan_chunks_adaptive(n_units, tiles, slots, window, floors, sm_count):
+    usual, small = floors
+    chunks = plan_chunks(n_units, tiles, slots, window, usual)
+    if tiles * chunks < sm_count and small < usual:
+        chunks = plan_chunks(n_units, tiles, slots, window, small)
+    return chunks
 
 
 def plan_chunks(n_units, tiles, slots, window, min_chunk):
@@ -553,6 +590,7 @@ def generate(program, domain, cfg):
                 e("for (int k = tid; k < {n}; k += {t}) spar{s}[k] = a{a}[ipar{s}[k]];".format(
                     n=len(param[3]), t=cfg.threads, s=slot, a=param[2]))
     e("__syncthreads();")
+    e("pdl_wait();                         // the grids may still be written by the preceding sweep")
     e()
 
     # ================================================================== producer warp
@@ -580,6 +618,10 @@ def generate(program, domain, cfg):
             e.close()
     e.close()
     e.close()   # for k
+    e("// all of this CTA's loads have landed: let the next sweep's CTAs be scheduled.  (Earlier would")
+    e("// place them while this grid still fills the SMs -- measured: unevenly, 20-35 % slower.)")
+    e("mbar_wait(&bar_full[(n_stages - 1) % {S}], ((n_stages - 1) / {S}) & 1);".format(S=S))
+    e("pdl_launch_dependents();")
     e("return;")
     e.close()   # producer
     e()
@@ -1111,7 +1153,7 @@ def make_plan(program, domain, device_props, options, override=None):
     tiles_x = -(-shape[-1] // cfg.TX)
     tiles_y = -(-shape[1] // cfg.TY) if rank == 3 else 1
     slots = device_props.sm_count * cfg.blocks_per_sm
-    min_chunk = max(4 * cfg.W, 16) if rank == 3 else max(4 * cfg.U, 64)
+    min_chunk = cfg.min_chunk
     static_smem = sum(a.size * 128 for a in table_plan(program, embedded)[3].values())
 
     def geometry(a0_begin, a0_end):
@@ -1121,7 +1163,7 @@ def make_plan(program, domain, device_props, options, override=None):
             launch.extra = (1,)
             return launch
         n_units = a0_end - a0_begin
-        chunks = plan_chunks(n_units, tiles_x * tiles_y, slots, cfg.W, min_chunk)
+        chunks = plan_chunks_adaptive(n_units, tiles_x * tiles_y, slots, cfg.W, min_chunk, device_props.sm_count)
         chunk_len = -(-n_units // chunks)
         if rank == 2:
             chunk_len = -(-chunk_len // cfg.U) * cfg.U if chunk_len > cfg.U else chunk_len

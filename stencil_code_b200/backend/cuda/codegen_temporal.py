@@ -62,6 +62,18 @@ def eligible(program, domain):
     return True, "star-in-z rank-3 stencil"
 
 
+def worthwhile(program, cfg):
+    """Does the fused kernel beat two single sweeps on this grid?  It is issue-bound, so its time
+    follows the points it computes, partial tiles included: measured on B200, 1024^2 planes
+    (83 % of the computed mid points useful) run 1.28x faster than two sweeps, 256^2 planes
+    (56 %) 0.86x.  Break-even is near 65 %."""
+    n0, n1, n2 = program.shape
+    tiles_x = -(-n2 // cfg.OUT_COLS)
+    tiles_y = -(-n1 // cfg.OUT_ROWS)
+    useful = n1 * n2 / float(tiles_y * cfg.MY * tiles_x * 128)
+    return useful >= 0.68
+
+
 def _tag(v):
     return "m{}".format(-v) if isinstance(v, int) and v < 0 else str(v)
 
@@ -199,6 +211,7 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     e("fence_barrier_init();")
     e.close()
     e("__syncthreads();")
+    e("pdl_wait();                         // the grid may still be written by the preceding sweep")
     e()
     # ------------------------------------------------------------------ producer
     e.open("if (warp == {})".format(NCW))
@@ -212,6 +225,8 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
         sf=SF, px=PADX, hy=HY, lo=c_lo[0], hi=c_hi[0]))
     e.close()
     e.close()
+    e("mbar_wait(&bar_full[(n_units - 1) % {S}], ((n_units - 1) / {S}) & 1);    // all loads have landed".format(S=S))
+    e("pdl_launch_dependents();")
     e("return;")
     e.close()
     e()

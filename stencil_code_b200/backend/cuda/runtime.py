@@ -68,6 +68,7 @@ SYMBOLS = {
     "sc_tensormap_tiled": (_I, [ctypes.POINTER(ScTmap), _VP, _I, _I, ctypes.POINTER(ctypes.c_uint64),
                                 ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), _I]),
     "sc_launch": (_I, [_VP, ctypes.c_char_p, _U32x3, _U32x3, _U32x3, ctypes.c_uint32, _VP, _PVP]),
+    "sc_launch_pingpong": (_I, [_VP, ctypes.c_char_p, _U32x3, _U32x3, ctypes.c_uint32, _VP, _PVP, _PVP, _I, ctypes.c_uint32]),
     "sc_stream_create": (_I, [_PVP]),
     "sc_stream_destroy": (_I, [_VP]),
     "sc_stream_synchronize": (_I, [_VP]),
@@ -453,7 +454,7 @@ class ConcreteCudaStencil(object):
                           peer_pointer, peer_shift)
 
     def _launch_plan(self, plan, module, arg_pointers, out_pointer, a0_begin, a0_end, stream,
-                     peer_pointer=0, peer_shift=0):
+                     peer_pointer=0, peer_shift=0, prepare_only=False):
         lo, hi = plan.domain.sweep_range
         a0_begin = lo if a0_begin is None else a0_begin
         a0_end = hi if a0_end is None else a0_end
@@ -484,6 +485,8 @@ class ConcreteCudaStencil(object):
             if len(self._launches) > 256:
                 self._launches.clear()
             self._launches[key] = prepared
+        if prepare_only:
+            return prepared
         _, pointers, grid, block, cluster, smem, name = prepared
         code = self._sc_launch(module.handle, name, grid, block, cluster, smem,
                                self.device.stream if stream is None else stream, pointers)
@@ -605,12 +608,17 @@ class ConcreteCudaStencil(object):
     # -- temporal blocking ----------------------------------------------------------------------
     def temporal(self):
         """(plan, module) of the fused two-sweep kernel, or None when the stencil is not eligible
-        (or STENCIL_CUDA_TEMPORAL=0)."""
+        or the grid's planes tile too poorly for it to pay (STENCIL_CUDA_TEMPORAL=0 turns it off,
+        =force skips the second test)."""
         if self._temporal is None:
             self._temporal = False
-            if os.environ.get("STENCIL_CUDA_TEMPORAL", "1") not in ("0", ""):
+            setting = os.environ.get("STENCIL_CUDA_TEMPORAL", "1")
+            if setting not in ("0", ""):
                 from . import codegen_temporal
                 ok, _ = codegen_temporal.eligible(self.program, self.plan.domain)
+                if ok and self.plan.strategy == 'stream' and setting != "force":
+                    ok = codegen_temporal.worthwhile(
+                        self.program, codegen_temporal.choose_config(self.program, self.device.planner_props()))
                 if ok and self.plan.strategy == 'stream':
                     plan = codegen_temporal.make_plan(self.program, self.plan.domain,
                                                       self.device.planner_props(), self.plan.options)
@@ -625,15 +633,30 @@ class ConcreteCudaStencil(object):
         pointer that holds the result."""
         current, spare = pointers_a, pointer_b
         fused = self.temporal()
+        stream = self.device.stream if stream is None else stream
         remaining = count
-        while remaining > 0:
-            if fused is not None and remaining >= 2:
-                self._launch_plan(fused[0], fused[1], [current] + table_pointers, spare, None, None, stream)
-                remaining -= 2
-            else:
-                self.launch([current] + table_pointers, spare, stream=stream)
-                remaining -= 1
-            current, spare = spare, current
+
+        def pingpong(plan, module, launches):
+            """`launches` launches alternating current->spare, spare->current, enqueued from C"""
+            even = self._launch_plan(plan, module, [current] + table_pointers, spare, None, None, stream,
+                                     prepare_only=True)
+            odd = self._launch_plan(plan, module, [spare] + table_pointers, current, None, None, stream,
+                                    prepare_only=True)
+            if even is None or launches <= 0:
+                return
+            _, pointers, grid, block, _, smem, name = even
+            programmatic = 0 if os.environ.get("STENCIL_CUDA_PDL", "1") in ("0", "") else 1
+            check(load_library().sc_launch_pingpong(module.handle, name, grid, block, smem, stream,
+                                                    pointers, odd[1], launches, programmatic), "iterated launch")
+        if fused is not None and remaining >= 2:
+            pingpong(fused[0], fused[1], remaining // 2)
+            if (remaining // 2) % 2:
+                current, spare = spare, current
+            remaining -= 2 * (remaining // 2)
+        if remaining > 0:
+            pingpong(self.plan, self.module, remaining)
+            if remaining % 2:
+                current, spare = spare, current
         return current
 
     # -- iterated application -------------------------------------------------------------------

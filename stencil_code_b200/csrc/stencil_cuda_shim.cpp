@@ -528,6 +528,38 @@ int sc_launch(sc_module* module, const char* function, const uint32_t grid[3],
     return SC_OK;
 }
 
+int sc_launch_pingpong(sc_module* module, const char* function, const uint32_t grid[3],
+                       const uint32_t block[3], uint32_t dynamic_smem, void* stream,
+                       void** args_even, void** args_odd, int count, uint32_t flags) {
+    if (!module || !function || !grid || !block || !args_even || !args_odd)
+        return fail(SC_EINVAL, "NULL argument");
+    CUfunction fn;
+    int rc = get_function(module, function, &fn);
+    if (rc != SC_OK) return rc;
+    rc = optin_smem(module, function, fn, dynamic_smem);
+    if (rc != SC_OK) return rc;
+    CUlaunchConfig config;
+    memset(&config, 0, sizeof config);
+    config.gridDimX = grid[0]; config.gridDimY = grid[1]; config.gridDimZ = grid[2];
+    config.blockDimX = block[0]; config.blockDimY = block[1]; config.blockDimZ = block[2];
+    config.sharedMemBytes = dynamic_smem;
+    config.hStream = reinterpret_cast<CUstream>(stream);
+    CUlaunchAttribute attribute;
+    memset(&attribute, 0, sizeof attribute);
+    if (flags & SC_LAUNCH_PROGRAMMATIC) {
+        attribute.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+        attribute.value.programmaticStreamSerializationAllowed = 1;
+        config.attrs = &attribute;
+        config.numAttrs = 1;
+    }
+    for (int i = 0; i < count; ++i) {
+        CUresult cu = g_drv.cuLaunchKernelEx_(&config, fn, (i & 1) ? args_odd : args_even, nullptr);
+        if (cu != CUDA_SUCCESS)
+            return cuda_fail(cu, (std::string("cuLaunchKernelEx(") + function + ")").c_str());
+    }
+    return SC_OK;
+}
+
 // ---- streams and events ------------------------------------------------------------------------
 int sc_stream_create(void** stream) {
     if (!stream) return fail(SC_EINVAL, "stream is NULL");

@@ -5,6 +5,8 @@ bit, and (small grid) the CPU oracle.
         --master-port 29511 tests/multi_gpu_check.py
 """
 import os
+
+os.environ.setdefault("STENCIL_CUDA_TEMPORAL", "force")     # the test planes are too small to be "worthwhile"
 import sys
 
 import numpy

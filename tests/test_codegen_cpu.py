@@ -53,7 +53,8 @@ def test_planner_picks_direct_for_small_and_stream_for_large(monkeypatch):
     monkeypatch.delenv("STENCIL_CUDA_STRATEGY", raising=False)
     from stencil_code_b200.library.laplacian import LaplacianKernel
     from stencil_code_b200.library.simple import SimpleKernel
-    assert make_plan(SimpleKernel(), [((1024, 1024), numpy.float32)]).strategy == 'direct'
+    assert make_plan(SimpleKernel(), [((512, 512), numpy.float32)]).strategy == 'direct'
+    assert make_plan(SimpleKernel(), [((1024, 1024), numpy.float32)]).strategy == 'stream'
     assert make_plan(SimpleKernel(), [(AUTO_STREAM_SHAPES[2], numpy.float32)]).strategy == 'stream'
     assert make_plan(LaplacianKernel(), [((24, 40, 128), numpy.float32)]).strategy == 'direct'
     assert make_plan(LaplacianKernel(), [(AUTO_STREAM_SHAPES[3], numpy.float32)]).strategy == 'stream'
@@ -196,6 +197,13 @@ def test_temporal_blocking_eligibility_and_compile():
             config = fused.notes['config']
             assert launch.grid[0] * config['OUT_COLS'] >= shape[2] and launch.grid[1] * config['OUT_ROWS'] >= shape[1]
     plan27 = make_plan(SpecializedLaplacian27(), [(shape, numpy.float32), ((4,), numpy.float32)], 'stream')
+    # planes that tile badly (256 columns = three 120-column tiles) are left to single sweeps
+    config = codegen_temporal.choose_config(plan.program, planner.B200)
+    verdicts = {}
+    for shape in ((64, 1024, 1024), (64, 256, 256), (64, 512, 512)):
+        program = type("P", (), dict(shape=shape))()
+        verdicts[shape] = codegen_temporal.worthwhile(program, config)
+    assert verdicts == {(64, 1024, 1024): True, (64, 256, 256): False, (64, 512, 512): True}
     assert not codegen_temporal.eligible(plan27.program, plan27.domain)[0]       # corner taps at dz != 0
     plan2d = make_plan(SimpleKernel(), [((2048, 2048), numpy.float32)], 'stream')
     assert not codegen_temporal.eligible(plan2d.program, plan2d.domain)[0]

@@ -202,7 +202,7 @@ def test_temporal_blocking_equals_separate_sweeps(mode, shape, monkeypatch):
     bit-identical to sweeping n times -- checked against the CPU oracle applied n times."""
     from stencil_code_b200.library.jacobi_3d import Jacobi3D
     from stencil_code_b200.library.laplacian import LaplacianKernel
-    monkeypatch.delenv("STENCIL_CUDA_TEMPORAL", raising=False)
+    monkeypatch.setenv("STENCIL_CUDA_TEMPORAL", "force")      # small planes: not "worthwhile"
     monkeypatch.setenv("STENCIL_CUDA_STRATEGY", "stream")
     for make in (lambda backend: Jacobi3D(1.0, 0.25, backend=backend, boundary_handling=mode),
                  lambda backend: LaplacianKernel(backend=backend, boundary_handling=mode)):
@@ -222,3 +222,33 @@ def test_temporal_blocking_equals_separate_sweeps(mode, shape, monkeypatch):
                          oracle_output(python_side, oracle_output(python_side, oracle_output(
                              python_side, oracle_output(python_side, grid)))))
     assert_bit_identical(tensor.cpu().numpy(), grid)          # the caller's tensor is not modified
+
+
+LONG_RUNS = [("direct", (40, 48, 64), 60), ("stream", (128, 128, 128), 40), ("stream", (24, 260, 512), 31),
+             ("direct", (300, 260), 60), ("stream", (1024, 1024), 40), ("stream", (700, 2052), 33)]
+
+
+@pytest.mark.parametrize("strategy,shape,sweeps", LONG_RUNS,
+                         ids=["{}-{}-x{}".format(s, "x".join(map(str, shape)), n) for s, shape, n in LONG_RUNS])
+def test_long_iterated_runs_with_programmatic_dependent_launch(strategy, shape, sweeps, monkeypatch):
+    """iterate(n) enqueues its sweeps from C with programmatic stream serialization: sweep k+1's CTAs
+    become resident while sweep k drains and hold at griddepcontrol.wait.  Small grids, where
+    several sweeps are in flight at once, are where an ordering bug would show: n sweeps must
+    equal the oracle applied n times, and the same run with the attribute off."""
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    from cases import OddWeights
+    monkeypatch.setenv("STENCIL_CUDA_STRATEGY", strategy)
+    monkeypatch.setenv("STENCIL_CUDA_TEMPORAL", "0")
+    make = (lambda backend: Jacobi3D(0.5, 0.0625, backend=backend)) if len(shape) == 3 else \
+        (lambda backend: OddWeights(backend=backend, boundary_handling='copy'))
+    grid = numpy.random.RandomState(23).random_sample(shape).astype(numpy.float32)
+    python_side = make('python')
+    expected = grid
+    for _ in range(sweeps):
+        expected = oracle_output(python_side, expected)
+    stencil = make('cuda')
+    assert stencil.specializer.specialize((grid,)).plan.strategy == strategy
+    for _ in range(3):                                  # timing-dependent bugs get three chances
+        assert_bit_identical(stencil.iterate(grid, sweeps), expected)
+    monkeypatch.setenv("STENCIL_CUDA_PDL", "0")
+    assert_bit_identical(stencil.iterate(grid, sweeps), expected)

@@ -3,6 +3,8 @@
 direct, stream rank 3 (clamp/zero/copy, partial tiles), stream rank 2 (two blocks per thread),
 tiled + re-rolled bilateral, fused two-sweep.  Each result is compared with the CPU oracle."""
 import os
+
+os.environ.setdefault("STENCIL_CUDA_TEMPORAL", "force")
 import sys
 
 import numpy
