@@ -620,8 +620,10 @@ def generate(program, domain, cfg):
     e.close()   # for k
     e("// all of this CTA's loads have landed: let the next sweep's CTAs be scheduled.  (Earlier would")
     e("// place them while this grid still fills the SMs -- measured: unevenly, 20-35 % slower.)")
+    e.lines.append("#ifdef SC_PDL")
     e("mbar_wait(&bar_full[(n_stages - 1) % {S}], ((n_stages - 1) / {S}) & 1);".format(S=S))
     e("pdl_launch_dependents();")
+    e.lines.append("#endif")
     e("return;")
     e.close()   # producer
     e()

@@ -225,8 +225,10 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
         sf=SF, px=PADX, hy=HY, lo=c_lo[0], hi=c_hi[0]))
     e.close()
     e.close()
+    e.lines.append("#ifdef SC_PDL")
     e("mbar_wait(&bar_full[(n_units - 1) % {S}], ((n_units - 1) / {S}) & 1);    // all loads have landed".format(S=S))
     e("pdl_launch_dependents();")
+    e.lines.append("#endif")
     e("return;")
     e.close()
     e()

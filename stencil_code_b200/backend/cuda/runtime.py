@@ -411,6 +411,7 @@ class ConcreteCudaStencil(object):
         self._tmaps = {}
         self._launches = {}
         self._temporal = None
+        self._pdl_modules = {}           # id(plan) -> module compiled with -DSC_PDL
         self._sc_launch = load_library().sc_launch
         self.last_duration = None        # seconds of the last call when STENCIL_CUDA_TIMING=1
 
@@ -627,6 +628,18 @@ class ConcreteCudaStencil(object):
                     self._temporal = (plan, module)
         return self._temporal or None
 
+    def _dependent_launch_module(self, plan):
+        """The plan's kernels compiled with -DSC_PDL (griddepcontrol instructions in), for launches
+        with programmatic stream serialization; built on the first iterate()."""
+        modules = self._pdl_modules
+        module = modules.get(id(plan))
+        if module is None:
+            module = compile_source(plan.source, "stencil_{}_pdl.cu".format(plan.strategy),
+                                    list(plan.options) + ["-DSC_PDL"])
+            module.load()
+            modules[id(plan)] = module
+        return module
+
     def sweeps(self, pointers_a, pointer_b, table_pointers, count, stream):
         """``count`` sweeps ping-ponging between device buffers a and b (a holds the input).
         Pairs of sweeps run as one fused launch where temporal blocking applies.  Returns the
@@ -636,8 +649,12 @@ class ConcreteCudaStencil(object):
         stream = self.device.stream if stream is None else stream
         remaining = count
 
+        programmatic = 0 if os.environ.get("STENCIL_CUDA_PDL", "1") in ("0", "") else 1
+
         def pingpong(plan, module, launches):
             """`launches` launches alternating current->spare, spare->current, enqueued from C"""
+            if programmatic:
+                module = self._dependent_launch_module(plan)
             even = self._launch_plan(plan, module, [current] + table_pointers, spare, None, None, stream,
                                      prepare_only=True)
             odd = self._launch_plan(plan, module, [spare] + table_pointers, current, None, None, stream,
@@ -645,7 +662,6 @@ class ConcreteCudaStencil(object):
             if even is None or launches <= 0:
                 return
             _, pointers, grid, block, _, smem, name = even
-            programmatic = 0 if os.environ.get("STENCIL_CUDA_PDL", "1") in ("0", "") else 1
             check(load_library().sc_launch_pingpong(module.handle, name, grid, block, smem, stream,
                                                     pointers, odd[1], launches, programmatic), "iterated launch")
         if fused is not None and remaining >= 2:

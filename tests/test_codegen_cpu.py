@@ -221,3 +221,28 @@ def test_slab_domain_constants():
     assert "if (out_peer)" in plan.source
     single = make_plan(Jacobi3D(), [((34, 64, 256), numpy.float32)], 'stream')
     assert "if (out_peer)" not in single.source        # the mirror store exists only in slab kernels
+
+
+def test_dependent_launch_variant_compiles_for_every_kernel_family(tmp_path):
+    """iterate() uses modules compiled with -DSC_PDL: same source, griddepcontrol instructions in
+    (SASS: PREEXIT = launch_dependents, ACQBULK = wait); the module for single calls has neither."""
+    import shutil
+    import subprocess
+    from stencil_code_b200.backend.cuda import codegen_temporal
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    from stencil_code_b200.library.simple import SimpleKernel
+    plans = [make_plan(Jacobi3D(), [((64, 96, 512), numpy.float32)], 'stream'),
+             make_plan(Jacobi3D(), [((64, 96, 512), numpy.float32)], 'direct'),
+             make_plan(SimpleKernel(), [((300, 1024), numpy.float32)], 'stream')]
+    plans.append(codegen_temporal.make_plan(plans[0].program, plans[0].domain, planner.B200, plans[0].options))
+    for plan in plans:
+        assert "pdl_wait();" in plan.source
+        plain = runtime.compile_source(plan.source, "plain.cu", plan.options).cubin()
+        dependent = runtime.compile_source(plan.source, "dependent.cu", list(plan.options) + ["-DSC_PDL"]).cubin()
+        assert plain != dependent
+        if shutil.which("cuobjdump"):
+            path = tmp_path / "k.cubin"
+            for data, expected in ((plain, False), (dependent, True)):
+                path.write_bytes(data)
+                sass = subprocess.run(["cuobjdump", "-sass", str(path)], capture_output=True, text=True).stdout
+                assert ("ACQBULK" in sass and "PREEXIT" in sass) == expected     # wait / launch_dependents
