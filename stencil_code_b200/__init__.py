@@ -8,6 +8,7 @@ from .stencil_exception import StencilException
 from .neighborhood import Neighborhood
 from .halo_enumerator import HaloEnumerator
 from .stencil_kernel import Stencil, SpecializedStencil, StencilArgConfig, product
+from .fusion import fuse, FusedStencils
 
 
 
@@ -19,5 +20,5 @@ def pinned_empty(shape, dtype='float32', device_index=None):
 
 
 __all__ = ['Stencil', 'SpecializedStencil', 'StencilArgConfig', 'StencilException',
-           'Neighborhood', 'HaloEnumerator', 'product', 'pinned_empty']
+           'Neighborhood', 'HaloEnumerator', 'product', 'pinned_empty', 'fuse', 'FusedStencils']
 __version__ = '0.1.0'

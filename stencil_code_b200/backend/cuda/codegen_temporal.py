@@ -62,6 +62,32 @@ def eligible(program, domain):
     return True, "star-in-z rank-3 stencil"
 
 
+def pair_eligible(first, first_domain, second, second_domain):
+    """Can ``second(first(grid))`` -- two DIFFERENT stencils -- run as one fused launch?  Each must
+    be eligible on its own, take the grid as its only argument (no tables: the two parameter lists
+    are not merged), and agree on shape and boundary mode."""
+    for program, domain in ((first, first_domain), (second, second_domain)):
+        ok, why = eligible(program, domain)
+        if not ok:
+            return False, why
+        if len(program.args) != 1:
+            return False, "stencils with table arguments are not fused with other stencils"
+        if domain.is_slab:
+            return False, "slab domains"
+    if first.shape != second.shape or first.boundary != second.boundary:
+        return False, "shape or boundary mode differ"
+    return True, "pair of star-in-z stencils"
+
+
+def _extents(program, second=None):
+    lo, hi = program.tap_extent()
+    hx, hy = max(-lo[2], hi[2]), max(-lo[1], hi[1])
+    if second is not None:
+        lo, hi = second.tap_extent()
+        hx, hy = max(hx, -lo[2], hi[2]), max(hy, -lo[1], hi[1])
+    return hx, hy
+
+
 def worthwhile(program, cfg):
     """Does the fused kernel beat two single sweeps on this grid?  It is issue-bound, so its time
     follows the points it computes, partial tiles included: measured on B200, 1024^2 planes
@@ -87,10 +113,9 @@ class TemporalConfig(object):
         return dict({k: getattr(self, k) for k in keys}, strategy="temporal2")
 
 
-def choose_config(program, device_props):
-    lo, hi = program.tap_extent()
-    hx = max(-lo[2], hi[2])
-    hy = max(-lo[1], hi[1])
+def choose_config(program, device_props, second=None):
+    # a pair of different stencils shares one tile geometry: halos sized for the wider of the two
+    hx, hy = _extents(program, second)
     PADX = 4 if hx else 0
     override = {}
     for item in filter(None, os.environ.get("STENCIL_CUDA_TEMPORAL_TILE", "").split(",")):
@@ -138,10 +163,15 @@ def choose_config(program, device_props):
     return best
 
 
-def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True):
+def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True, second=None,
+             second_domain=None):
     """CUDA source of the fused kernel.  ``mirror``: also store results through ``out_peer`` (slab
-    boundary launches); defaults to ``domain.is_slab``."""
+    boundary launches); defaults to ``domain.is_slab``.  ``second``: the program of the second
+    sweep when it is another stencil than the first (``fuse(a, b)``); its halo (``zero``/``copy``)
+    follows ``second_domain``, i.e. its own ghost depth."""
     mirror = domain.is_slab if mirror is None else mirror
+    second = program if second is None else second
+    second_domain = domain if second_domain is None else second_domain
     shape = program.shape
     N0, N1, N2 = shape
     MY, BY, NCW, S = cfg.MY, cfg.BY, cfg.NCW, cfg.S
@@ -152,6 +182,8 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     clamp, copy = boundary == 'clamp', boundary == 'copy'
     c_lo, c_hi = domain.clamp_lo, domain.clamp_hi
     i_lo, i_hi = domain.interior_lo, domain.interior_hi
+    j_lo, j_hi = second_domain.interior_lo, second_domain.interior_hi      # second sweep's interior
+    two_masks = (tuple(i_lo), tuple(i_hi)) != (tuple(j_lo), tuple(j_hi))
     fp = Footprint(program, BY, copy)
     _, const_refs, _, _ = table_plan(program, False)
     clamp_rows = clamp and HY > 0
@@ -238,7 +270,8 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     e("const int gx = x0 + lane * 4;             // first column of this thread's block")
     e("const int sbase_in = ({} + tr * {}) * {} + {} + lane * 4;".format(HY, BY, PITCH, PADX))
     e("const int sbase_mid = tr * {} * {} + lane * 4;".format(BY, MP))
-    rows_needed = sorted({k[1] for k in fp.ages})
+    rows_needed = sorted({k[1] for k in fp.ages} |
+                         {b + _tap3(tap.offset)[1] for tap in second.taps() for b in range(BY)})
     if clamp_rows:
         for row in rows_needed:
             e("const int rd{t} = min(max(gy + ({r}), 0), {n}) - (gy + ({r}));   // clamped row delta".format(
@@ -260,6 +293,21 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                     tests.append("gx + {} >= {}".format(j, i_hi[2]))
                 if tests:
                     e("if ({}) halo_mask |= {}u;".format(" || ".join(tests), 1 << (b * 4 + j)))
+        if two_masks:
+            e("u32 halo_mask2 = 0;                  // the same for the second stencil's ghost depth")
+            for b in range(BY):
+                for j in range(4):
+                    tests = []
+                    if j_lo[1] > 0:
+                        tests.append("gy + {} < {}".format(b, j_lo[1]))
+                    if j_hi[1] < N1:
+                        tests.append("gy + {} >= {}".format(b, j_hi[1]))
+                    if j_lo[2] > 0:
+                        tests.append("gx + {} < {}".format(j, j_lo[2]))
+                    if j_hi[2] < N2:
+                        tests.append("gx + {} >= {}".format(j, j_hi[2]))
+                    if tests:
+                        e("if ({}) halo_mask2 |= {}u;".format(" || ".join(tests), 1 << (b * 4 + j)))
     # which of this thread's outputs are inside the valid (interior) part of the mid tile and the grid
     lane_ok = "lane >= 1 && lane <= 30 && " if HX else ""
     e("const bool col_ok = {}gx >= 0 && gx < {};".format(lane_ok, N2))
@@ -373,7 +421,7 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
         # other rows of the thread's own block, because a block row outside the grid must read as
         # the clamped row (the buffer read goes through the clamped row offset, a register would not)
         by_row = {}
-        for tap in program.taps():
+        for tap in second.taps():
             dz, dy, dx = _tap3(tap.offset)
             if dz != 0:
                 continue
@@ -415,7 +463,7 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
         acc = [["acc{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
         for b in range(BY):
             e("float {};".format(", ".join(n + " = 0.0f" for n in acc[b])))
-        for statement in program.statements:
+        for statement in second.statements:
             for b in range(BY):
                 for j in range(4):
                     def tap_text(tap, b=b, j=j):
@@ -426,22 +474,23 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                         if clamp:
                             return "({} ? {} : {})".format("z_lo" if dz < 0 else "z_hi", mid_own(phase, 0, b, j), own)
                         return own
-                    single = pp.PointProgram(3, shape, program.out_ctype, program.args, [statement],
-                                             program.ghost_depth, boundary)
+                    single = pp.PointProgram(3, shape, second.out_ctype, second.args, [statement],
+                                             second.ghost_depth, boundary)
                     e(emit_statements(single, tap_text, table_text, acc=acc[b][j], indent="")[0])
         if not clamp:
+            mask2 = "halo_mask2" if two_masks else "halo_mask"
             ztests = []
-            if i_lo[0] > 0:
-                ztests.append("zo < {}".format(i_lo[0]))
-            if i_hi[0] < N0:
-                ztests.append("zo >= {}".format(i_hi[0]))
+            if j_lo[0] > 0:
+                ztests.append("zo < {}".format(j_lo[0]))
+            if j_hi[0] < N0:
+                ztests.append("zo >= {}".format(j_hi[0]))
             e("const bool zo_halo = {};".format(" || ".join(ztests) if ztests else "false"))
-            e.open("if (zo_halo || halo_mask)")
+            e.open("if (zo_halo || {})".format(mask2))
             for b in range(BY):
                 for j in range(4):
                     # 'copy': the halo of sweep 2 copies the halo of mid, which copied the input
                     value = mid_own(phase, 0, b, j) if copy else "0.0f"
-                    e("if (zo_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), acc[b][j], value))
+                    e("if (zo_halo || ({} & {}u)) {} = {};".format(mask2, 1 << (b * 4 + j), acc[b][j], value))
             e.close()
         for b in range(BY):
             row_ok = "tr * {by} + {b} >= {hy} && tr * {by} + {b} < {hi} && gy + {b} >= 0 && gy + {b} < {n1}".format(
@@ -461,15 +510,19 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     return e.text()
 
 
-def make_plan(program, domain, device_props, options):
-    """CudaPlan-like record for the fused two-sweep kernel (launched by ``iterate``)."""
+def make_plan(program, domain, device_props, options, second=None, second_domain=None):
+    """CudaPlan-like record for the fused two-sweep kernel (launched by ``iterate``; with
+    ``second`` by ``fuse(first, second)``)."""
     from .transformer import CudaPlan
     from .planner import Launch
-    ok, why = eligible(program, domain)
+    if second is None:
+        ok, why = eligible(program, domain)
+    else:
+        ok, why = pair_eligible(program, domain, second, second_domain)
     if not ok:
         raise StencilException("temporal blocking not applicable: " + why)
-    cfg = choose_config(program, device_props)
-    source = generate(program, domain, cfg)
+    cfg = choose_config(program, device_props, second)
+    source = generate(program, domain, cfg, second=second, second_domain=second_domain)
     if domain.is_slab:
         # interior launches of a slab never mirror: a second entry point without that code
         # (the kernel is issue bound; the unused mirror stores cost about 6 %)

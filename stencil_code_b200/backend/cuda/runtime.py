@@ -412,6 +412,7 @@ class ConcreteCudaStencil(object):
         self._launches = {}
         self._temporal = None
         self._pdl_modules = {}           # id(plan) -> module compiled with -DSC_PDL
+        self._pairs = {}                 # id(other concrete stencil) -> (other, fused (plan, module) or None)
         self._sc_launch = load_library().sc_launch
         self.last_duration = None        # seconds of the last call when STENCIL_CUDA_TIMING=1
 
@@ -461,7 +462,7 @@ class ConcreteCudaStencil(object):
         a0_end = hi if a0_end is None else a0_end
         if a0_end <= a0_begin:
             return
-        key = (plan.strategy, tuple(arg_pointers), out_pointer, a0_begin, a0_end, peer_pointer, peer_shift)
+        key = (id(plan), tuple(arg_pointers), out_pointer, a0_begin, a0_end, peer_pointer, peer_shift)
         prepared = self._launches.get(key)
         if prepared is None:
             values = [ctypes.c_void_p(pointer) for pointer in arg_pointers]
@@ -627,6 +628,32 @@ class ConcreteCudaStencil(object):
                     module.load()
                     self._temporal = (plan, module)
         return self._temporal or None
+
+    def pair_with(self, other):
+        """(plan, module) of ONE launch computing ``other(self(grid))`` -- the fused two-sweep kernel
+        with a different stencil in each sweep (``fusion.fuse``) -- or None when the pair is not
+        eligible, its tiles would not pay, or STENCIL_CUDA_TEMPORAL=0."""
+        entry = self._pairs.get(id(other))
+        if entry is None:
+            from . import codegen_temporal
+            found = None
+            setting = os.environ.get("STENCIL_CUDA_TEMPORAL", "1")
+            if setting not in ("0", "") and self.plan.strategy == 'stream' and other.plan.strategy == 'stream':
+                ok, _ = codegen_temporal.pair_eligible(self.program, self.plan.domain,
+                                                       other.program, other.plan.domain)
+                props = self.device.planner_props()
+                if ok and setting != "force":
+                    ok = codegen_temporal.worthwhile(
+                        self.program, codegen_temporal.choose_config(self.program, props, other.program))
+                if ok:
+                    plan = codegen_temporal.make_plan(self.program, self.plan.domain, props, self.plan.options,
+                                                      second=other.program, second_domain=other.plan.domain)
+                    module = compile_source(plan.source, "stencil_pair.cu", plan.options)
+                    module.load()
+                    found = (plan, module)
+            entry = (other, found)                   # keeps `other` alive: its id is the key
+            self._pairs[id(other)] = entry
+        return entry[1]
 
     def _dependent_launch_module(self, plan):
         """The plan's kernels compiled with -DSC_PDL (griddepcontrol instructions in), for launches

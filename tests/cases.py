@@ -64,6 +64,20 @@ class Radius2Cross3D(Stencil):
                 out_grid[x] += weights[self.distance(x, y)] * in_grid[y]
 
 
+class WideStar3D(Stencil):
+    """Star in z with in-plane reach 2 (ghost depth (1, 2, 2)): fused with a radius-1 stencil, the
+    two stages have different halos."""
+    neighborhoods = [[(1, 0, 0), (-1, 0, 0)], [(0, -2, 0), (0, 2, 0), (0, 0, -2), (0, 0, 2), (0, 1, 1)]]
+
+    def kernel(self, in_grid, out_grid):
+        for x in self.interior_points(out_grid):
+            out_grid[x] = 0.5 * in_grid[x]
+            for y in self.neighbors(x, 0):
+                out_grid[x] += 0.125 * in_grid[y]
+            for y in self.neighbors(x, 1):
+                out_grid[x] -= 0.0625 * in_grid[y]
+
+
 CONV5 = numpy.array([[1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, -4, 1, 3],
                      [1, 1, 1, 1, 1], [1, 1, 1, 7, 1]])        # test/test_c_end_to_end.py:49-57
 CONV5_BENCH = numpy.array([[1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, -4, 1, 1],
