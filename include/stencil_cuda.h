@@ -153,6 +153,11 @@ int         sc_memset32_async(void* device_ptr, uint32_t value, size_t count, vo
 int         sc_memcpy_h2d_async(void* device_dst, const void* host_src, size_t bytes, void* stream);
 int         sc_memcpy_d2h_async(void* host_dst, const void* device_src, size_t bytes, void* stream);
 int         sc_memcpy_d2d_async(void* device_dst, const void* device_src, size_t bytes, void* stream);
+/* `height` rows of `width_bytes`, row r at dst + r*dst_pitch <- src + r*src_pitch; either side host
+ * or device memory (unified addressing).  Packs a grid whose rows are no multiple of 16 bytes
+ * into the padded row pitch the TMA kernels need, and unpacks the result.                        */
+int         sc_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                              size_t width_bytes, size_t height, void* stream);
 int         sc_host_alloc(void** host_ptr, size_t bytes);      /* page-locked, portable          */
 int         sc_host_free(void* host_ptr);
 int         sc_host_register(void* host_ptr, size_t bytes);    /* pin an existing allocation     */

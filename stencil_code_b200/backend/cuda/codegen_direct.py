@@ -10,6 +10,7 @@ Every output element in the requested axis-0 range is written exactly once, so t
 needs no zero-fill beforehand (the reference's ``zeros`` allocation, ``stencil_kernel.py:412-416``,
 is folded into the kernel: the accumulator starts at 0).
 """
+from ...stencil_exception import StencilException
 from .codegen_common import PROLOGUE, ctype_zero, emit_statements
 
 BLOCK_THREADS = 256
@@ -62,6 +63,8 @@ def generate(program, domain):
     for s in shape[1:]:
         per0 *= s
 
+    if domain.is_pitched:
+        raise StencilException("the one-thread-per-point kernel addresses dense rows only")
     lines = [PROLOGUE]
     lines.append('extern "C" __global__ void __launch_bounds__({})'.format(BLOCK_THREADS))
     lines.append("stencil_direct({})".format(", ".join(params)))

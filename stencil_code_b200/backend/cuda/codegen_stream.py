@@ -120,8 +120,8 @@ def applicable(program, domain, device_props, forced=False):
         if arg.ctype != pp.FLOAT:
             return False, "grid argument '{}' is not float32".format(arg.name)
     n_fast = program.shape[-1]
-    if n_fast % 4 != 0:
-        return False, "rows of {} floats are not a multiple of 16 bytes (TMA stride rule)".format(n_fast)
+    if domain.row_pitch % 4 != 0:
+        return False, "rows of {} floats are not a multiple of 16 bytes (TMA stride rule)".format(domain.row_pitch)
     if n_fast < 32:
         return False, "rows shorter than 32 floats"
     if program.dim == 3 and program.shape[1] < 4:
@@ -212,11 +212,16 @@ class Footprint(object):
             for b in range(BY):
                 for j in range(4):
                     self.ages.setdefault((0, b, j), set()).add(0)
+        # rows of the grid that end inside a thread's quad of columns (length no multiple of 4:
+        # only reachable through the padded-row buffers of iterate())
+        self.ragged = program.shape[-1] % 4 != 0
         if program.boundary == 'clamp':
             # a column left of the grid takes the value of its right-hand neighbour (and vice versa
             # on the right), cascading up to the thread's own columns: those must be loaded too
+            # (ragged rows: the cascade on the right can start inside the quad, at column 0)
+            first_right = 0 if self.ragged else 3
             for (g, row, col), ages in list(self.ages.items()):
-                inner = range(col + 1, 1) if col < 0 else range(3, col) if col > 3 else ()
+                inner = range(col + 1, 1) if col < 0 else range(first_right, col) if col > 3 else ()
                 for c in inner:
                     self.ages.setdefault((g, row, c), set()).update(ages)
         all_ages = [a for s in self.ages.values() for a in s] or [0]
@@ -690,7 +695,7 @@ def generate(program, domain, cfg):
         """cascade the nearest in-grid column outward (names_by_col: col -> register name)"""
         base = col_base(row if rank == 2 else 0)
         left = sorted((c for c in names_by_col if c < 0), reverse=True)
-        right = sorted(c for c in names_by_col if c > 3)
+        right = sorted(c for c in names_by_col if c > (0 if fp.ragged else 3))
         for c in left:
             e("if ({} + ({}) < 0) {} = {};".format(base, c, names_by_col[c], names_by_col[c + 1]))
         for c in right:
@@ -961,10 +966,10 @@ def generate(program, domain, cfg):
         for b in range(BY):
             if rank == 3:
                 cond = "col_ok && gy + {} < row_end".format(b)
-                address = "out + ((i64)z * {} + (gy + {})) * {} + gx".format(N1, b, N2)
+                address = "out + ((i64)z * {} + (gy + {})) * {} + gx".format(N1, b, domain.row_pitch)
             else:
                 cond = "col_ok{}".format(b)
-                address = "out + (i64)z * {} + {}".format(N2, col_base(b))
+                address = "out + (i64)z * {} + {}".format(domain.row_pitch, col_base(b))
             e.open("if ({})".format(cond))
             e("float* const dst = {};".format(address))
             e("st_global_v4(dst, {});".format(", ".join(acc[b])))
@@ -1135,7 +1140,7 @@ def make_plan(program, domain, device_props, options, override=None):
     embedded = wants_plane_embedding(program, domain)
     if embedded:
         program = embed_as_plane(program)
-        domain3 = Domain(program.shape, program.ghost_depth)
+        domain3 = Domain(program.shape, program.ghost_depth, row_pitch=domain.row_pitch)
         cfg = choose_config(program, domain3, device_props, dict(override or {}, embedded=True))
         source = generate(program, domain3, cfg)
     else:
@@ -1143,15 +1148,16 @@ def make_plan(program, domain, device_props, options, override=None):
         source = generate(program, domain, cfg)
     rank = cfg.rank
     shape = program.shape
+    row_pitch = domain.row_pitch             # elements between row starts (== shape[-1] unless padded)
     specs = []
     for arg in _grid_args(program):
         if rank == 3:
             n0, n1, n2 = shape
-            specs.append(TensorMapSpec(arg.index, (n2, n1, n0), (n2 * 4, n1 * n2 * 4),
+            specs.append(TensorMapSpec(arg.index, (n2, n1, n0), (row_pitch * 4, n1 * row_pitch * 4),
                                        (cfg.PITCH, cfg.ROWS, 1), tag="tile"))
         else:
             n0, n1 = shape
-            specs.append(TensorMapSpec(arg.index, (n1, n0), (n1 * 4,), (cfg.PITCH, cfg.U), tag="block"))
+            specs.append(TensorMapSpec(arg.index, (n1, n0), (row_pitch * 4,), (cfg.PITCH, cfg.U), tag="block"))
     tiles_x = -(-shape[-1] // cfg.TX)
     tiles_y = -(-shape[1] // cfg.TY) if rank == 3 else 1
     slots = device_props.sm_count * cfg.blocks_per_sm

@@ -40,7 +40,7 @@ def eligible(program, domain):
     grids = _grid_args(program)
     if len(grids) != 1 or grids[0].index != 0 or grids[0].ctype != pp.FLOAT:
         return False, "exactly one float32 grid argument"
-    if program.shape[-1] % 4 or program.shape[-1] < 256 or program.shape[1] < 16 or program.shape[0] < 8:
+    if domain.row_pitch % 4 or program.shape[-1] < 256 or program.shape[1] < 16 or program.shape[0] < 8:
         return False, "grid too small or rows not 16-byte multiples"
     if domain.is_slab and domain.slab_ghost < 2 * program.ghost_depth[0]:
         return False, "slab carries fewer than two ghost depths of planes"
@@ -322,10 +322,11 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
         e("float {};".format(", ".join(n + " = 0.0f" for n in names[first:first + 8])))
     counter = [0]
 
-    def column_fix(names_by_col):
+    def column_fix(names_by_col, in_quad=False):
+        """``in_quad``: rows that end inside the quad (ragged grids): start the cascade at column 1"""
         for c in sorted((c for c in names_by_col if c < 0), reverse=True):
             e("if (gx + ({}) < 0) {} = {};".format(c, names_by_col[c], names_by_col[c + 1]))
-        for c in sorted(c for c in names_by_col if c > 3):
+        for c in sorted(c for c in names_by_col if c > (0 if in_quad else 3)):
             e("if (gx + {} > {}) {} = {};".format(c, N2 - 1, names_by_col[c], names_by_col[c - 1]))
 
     def load_rows(pointer, pitch, by_row, name_of_col, declare):
@@ -371,7 +372,8 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                     outer = [c for c in by_row[row] if c < 0 or c > 3]
                     if outer:
                         span = range(min(min(outer), 0), max(max(outer), 3) + 1)
-                        column_fix({c: in_name(phase, age, row, c) for c in span if (0, row, c) in fp.ages})
+                        column_fix({c: in_name(phase, age, row, c) for c in span if (0, row, c) in fp.ages},
+                                   in_quad=fp.ragged)
                 e.close()
         release_back = 1 - min(max(s) for s in fp.ages.values())
         e("__syncwarp();")
@@ -404,6 +406,12 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                 for j in range(4):
                     value = in_name(phase, 0, b, j) if copy else "0.0f"
                     e("if (zm_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), macc[b][j], value))
+            e.close()
+        if clamp_cols and fp.ragged:
+            # the intermediate grid's columns past the last one read as the last one
+            e.open("if (x_edge)")
+            for b in range(BY):
+                column_fix({j: macc[b][j] for j in range(4)}, in_quad=True)
             e.close()
         e("float* const mid_new = mid + (unit % 3) * {} + sbase_mid;".format(MF))
         for b in range(BY):
@@ -496,7 +504,7 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
             row_ok = "tr * {by} + {b} >= {hy} && tr * {by} + {b} < {hi} && gy + {b} >= 0 && gy + {b} < {n1}".format(
                 by=BY, b=b, hy=HY, hi=MY - HY, n1=N1)
             e.open("if (col_ok && {})".format(row_ok))
-            e("float* const dst = out + ((i64)zo * {} + (gy + {})) * {} + gx;".format(N1, b, N2))
+            e("float* const dst = out + ((i64)zo * {} + (gy + {})) * {} + gx;".format(N1, b, domain.row_pitch))
             e("st_global_v4(dst, {});".format(", ".join(acc[b])))
             if mirror:                  # slab boundary launches also fill the neighbour's ghost planes
                 e("if (out_peer) st_global_v4(out_peer + (dst - out) + peer_shift, {});".format(", ".join(acc[b])))
@@ -528,7 +536,9 @@ def make_plan(program, domain, device_props, options, second=None, second_domain
         # (the kernel is issue bound; the unused mirror stores cost about 6 %)
         source += generate(program, domain, cfg, function=FUNCTION + "_interior", mirror=False, prologue=False)
     n0, n1, n2 = program.shape
-    specs = [TensorMapSpec(0, (n2, n1, n0), (n2 * 4, n1 * n2 * 4), (cfg.PITCH, cfg.ROWS, 1), tag="temporal")]
+    row_pitch = domain.row_pitch
+    specs = [TensorMapSpec(0, (n2, n1, n0), (row_pitch * 4, n1 * row_pitch * 4), (cfg.PITCH, cfg.ROWS, 1),
+                           tag="temporal")]
     tiles_x = -(-n2 // cfg.OUT_COLS)
     tiles_y = -(-n1 // cfg.OUT_ROWS)
     slots = device_props.sm_count * cfg.blocks_per_sm

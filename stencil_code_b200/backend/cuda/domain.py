@@ -9,15 +9,21 @@ are compile-time constants of the generated kernel.
 
 
 class Domain(object):
-    def __init__(self, shape, ghost_depth, open_lo=False, open_hi=False, slab_ghost=None):
+    def __init__(self, shape, ghost_depth, open_lo=False, open_hi=False, slab_ghost=None, row_pitch=None):
         """
         :param shape: shape of the LOCAL array (ghost planes included when a face is open)
         :param ghost_depth: per-dimension ghost depth of the stencil
         :param open_lo / open_hi: axis-0 faces that border another slab
         :param slab_ghost: ghost planes per side of a slab (default: the stencil's axis-0 ghost
             depth; twice that when pairs of sweeps are fused between exchanges)
+        :param row_pitch: elements between the starts of consecutive rows of every grid buffer
+            (default: the row length).  iterate() keeps grids whose rows are no multiple of
+            16 bytes in buffers with padded rows, which is what lets TMA address them.
         """
         self.shape = tuple(int(s) for s in shape)
+        self.row_pitch = int(row_pitch) if row_pitch else self.shape[-1]
+        if self.row_pitch < self.shape[-1]:
+            raise ValueError("row pitch shorter than a row")
         self.ghost = tuple(int(g) for g in ghost_depth)
         self.open_lo, self.open_hi = bool(open_lo), bool(open_hi)
         dim = len(self.shape)
@@ -55,4 +61,8 @@ class Domain(object):
         return self.data_lo[0], self.data_hi[0] + 1
 
     def key(self):
-        return (self.shape, self.ghost, self.open_lo, self.open_hi, self.slab_ghost)
+        return (self.shape, self.ghost, self.open_lo, self.open_hi, self.slab_ghost, self.row_pitch)
+
+    @property
+    def is_pitched(self):
+        return self.row_pitch != self.shape[-1]

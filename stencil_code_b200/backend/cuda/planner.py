@@ -41,6 +41,8 @@ def plan(program, domain, device_props=None, forced_strategy=None, options=()):
     device_props = device_props or B200
     strategy = forced_strategy
     reason = "forced" if forced_strategy else None
+    if domain.is_pitched:
+        strategy = 'stream'              # padded rows exist only for the TMA kernels (iterate())
     if strategy is None:
         from . import codegen_stream
         ok, reason = codegen_stream.applicable(program, domain, device_props)

@@ -85,6 +85,7 @@ SYMBOLS = {
     "sc_memcpy_h2d_async": (_I, [_VP, _VP, _SZ, _VP]),
     "sc_memcpy_d2h_async": (_I, [_VP, _VP, _SZ, _VP]),
     "sc_memcpy_d2d_async": (_I, [_VP, _VP, _SZ, _VP]),
+    "sc_memcpy2d_async": (_I, [_VP, _SZ, _VP, _SZ, _SZ, _SZ, _VP]),
     "sc_host_alloc": (_I, [_PVP, _SZ]),
     "sc_host_free": (_I, [_VP]),
     "sc_host_register": (_I, [_VP, _SZ]),
@@ -399,6 +400,13 @@ def _is_torch_tensor(obj):
     return hasattr(obj, "data_ptr") and hasattr(obj, "is_cuda")
 
 
+def _device_tensors(args):
+    """contiguous tensors on the grid's device for every argument (tables may arrive as numpy)"""
+    import torch
+    device = args[0].device
+    return [(arg if _is_torch_tensor(arg) else torch.as_tensor(arg)).to(device).contiguous() for arg in args]
+
+
 class ConcreteCudaStencil(object):
     """A compiled, launchable specialisation (what ``SpecializedStencil.finalize`` returns)."""
 
@@ -412,6 +420,7 @@ class ConcreteCudaStencil(object):
         self._launches = {}
         self._temporal = None
         self._pdl_modules = {}           # id(plan) -> module compiled with -DSC_PDL
+        self._twin = None                # specialisation over padded rows (see _pitched_twin)
         self._pairs = {}                 # id(other concrete stencil) -> (other, fused (plan, module) or None)
         self._sc_launch = load_library().sc_launch
         self.last_duration = None        # seconds of the last call when STENCIL_CUDA_TIMING=1
@@ -524,10 +533,7 @@ class ConcreteCudaStencil(object):
         if grid.device.index != self.device.index:
             raise StencilException("tensor is on cuda:{} but the stencil was specialised on cuda:{}"
                                    .format(grid.device.index, self.device.index))
-        tensors = []
-        for arg in args:
-            tensor = arg if _is_torch_tensor(arg) else torch.as_tensor(arg)
-            tensors.append(tensor.to(grid.device).contiguous())
+        tensors = _device_tensors(args)
         result = torch.empty_like(tensors[0]) if out is None else out
         if not result.is_contiguous():
             raise StencilException("out= must be contiguous")
@@ -629,6 +635,72 @@ class ConcreteCudaStencil(object):
                     self._temporal = (plan, module)
         return self._temporal or None
 
+    # -- grids whose rows are no multiple of 16 bytes ---------------------------------------------
+    def _pitched_twin(self):
+        """The sibling specialisation that works on buffers with rows padded to a multiple of 16
+        bytes, or None.  TMA cannot address a grid of, say, 513^3 floats (its row stride must be a
+        multiple of 16 bytes), so single calls on such grids take the one-thread-per-point kernel;
+        iterate() packs the grid into padded rows once (``sc_memcpy2d_async``), runs all its
+        sweeps there at full speed and unpacks the result."""
+        if self._twin is None:
+            self._twin = False
+            program, origin = self.program, getattr(self, 'origin', None)
+            width = program.shape[-1]
+            from .codegen_stream import _grid_args
+            if (origin is not None and width % 4 and program.dim in (2, 3) and program.out_ctype == 'float'
+                    and len(_grid_args(program)) == 1 and not self.plan.domain.is_slab
+                    and not self.plan.domain.is_pitched
+                    and os.environ.get("STENCIL_CUDA_PITCHED", "1") not in ("0", "")
+                    and os.environ.get("STENCIL_CUDA_STRATEGY") in (None, "", "stream")):
+                try:
+                    twin = origin[0].specialize_config(origin[1], row_pitch=-(-width // 4) * 4)
+                    if twin.plan.strategy == 'stream':
+                        self._twin = twin
+                except StencilException:
+                    pass
+        return self._twin or None
+
+    def _iterate_pitched(self, twin, args, iterations):
+        library = load_library()
+        device = self.device
+        shape = self.program.shape
+        width, pitch = shape[-1], twin.plan.domain.row_pitch
+        rows = 1
+        for extent in shape[:-1]:
+            rows *= extent
+
+        def copy2d(dst, dst_pitch, src, src_pitch, stream):
+            check(library.sc_memcpy2d_async(ctypes.c_void_p(dst), dst_pitch * 4, ctypes.c_void_p(src),
+                                            src_pitch * 4, width * 4, rows, stream), "pitched copy")
+        if _is_torch_tensor(args[0]):
+            import torch
+            stream = ctypes.c_void_p(torch.cuda.current_stream(args[0].device).cuda_stream)
+            tensors = _device_tensors(args)
+            first = torch.empty(rows * pitch, dtype=tensors[0].dtype, device=tensors[0].device)
+            second = torch.empty_like(first)
+            copy2d(first.data_ptr(), pitch, tensors[0].data_ptr(), width, stream)
+            final = twin.sweeps(first.data_ptr(), second.data_ptr(), [t.data_ptr() for t in tensors[1:]],
+                                iterations, stream)
+            result = torch.empty_like(tensors[0])
+            copy2d(result.data_ptr(), width, final, pitch, stream)
+            return result
+        check(library.sc_set_device(device.index))
+        stream = device.stream
+        arrays = [numpy.ascontiguousarray(a) for a in args]
+        first, second = device.alloc(rows * pitch * 4), device.alloc(rows * pitch * 4)
+        tables = [device.alloc(a.nbytes) for a in arrays[1:]]
+        copy2d(first.ptr, pitch, arrays[0].ctypes.data, width, stream)
+        for array, buffer in zip(arrays[1:], tables):
+            check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(array.ctypes.data),
+                                              array.nbytes, stream))
+        final = twin.sweeps(first.ptr, second.ptr, [b.ptr for b in tables], iterations, stream)
+        result = device.pinned_empty(arrays[0].shape, arrays[0].dtype)
+        copy2d(result.ctypes.data, width, final, pitch, stream)
+        device.synchronize(stream)
+        for buffer in tables + [first, second]:
+            buffer.release()
+        return result
+
     def pair_with(self, other):
         """(plan, module) of ONE launch computing ``other(self(grid))`` -- the fused two-sweep kernel
         with a different stencil in each sweep (``fusion.fuse``) -- or None when the pair is not
@@ -712,10 +784,13 @@ class ConcreteCudaStencil(object):
         self._check_args(args)
         library = load_library()
         device = self.device
+        twin = self._pitched_twin() if iterations >= 1 else None
+        if twin is not None:
+            return self._iterate_pitched(twin, args, iterations)
         if _is_torch_tensor(grid):
             import torch
             stream = ctypes.c_void_p(torch.cuda.current_stream(grid.device).cuda_stream)
-            tensors = [t.contiguous() for t in args]
+            tensors = _device_tensors(args)
             if iterations == 0:
                 return grid.clone()
             first = torch.empty_like(tensors[0])

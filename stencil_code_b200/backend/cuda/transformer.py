@@ -54,12 +54,13 @@ NVRTC_OPTIONS = (
 class StencilCudaTransformer(StencilBackend):
     def __init__(self, input_grids=None, output_grid=None, kernel=None, arg_cfg=None,
                  fusable_nodes=None, testing=False, open_faces=(False, False), device_props=None,
-                 strategy=None, slab_ghost=None):
+                 strategy=None, slab_ghost=None, row_pitch=None):
         super(StencilCudaTransformer, self).__init__(
             input_grids, output_grid, kernel, arg_cfg=arg_cfg, fusable_nodes=fusable_nodes,
             testing=testing)
         self.open_faces = open_faces
         self.slab_ghost = slab_ghost
+        self.row_pitch = row_pitch
         self.device_props = device_props
         self.forced_strategy = strategy or os.environ.get("STENCIL_CUDA_STRATEGY") or None
 
@@ -92,7 +93,8 @@ class StencilCudaTransformer(StencilBackend):
 
     def visit_InteriorPointsLoop(self, node):
         program = self.build_program(node)
-        domain = Domain(program.shape, program.ghost_depth, *self.open_faces, slab_ghost=self.slab_ghost)
+        domain = Domain(program.shape, program.ghost_depth, *self.open_faces, slab_ghost=self.slab_ghost,
+                        row_pitch=self.row_pitch)
         for d in range(program.dim):
             if domain.interior_hi[d] <= domain.interior_lo[d] and program.boundary != 'clamp' \
                     and program.shape[d] < 2 * program.ghost_depth[d]:

@@ -49,7 +49,7 @@ int fail(int code, const char* fmt, ...) {
     X(cuStreamWaitValue32) X(cuStreamWriteValue32) X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent) \
     X(cuEventCreate) X(cuEventDestroy) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) \
     X(cuMemAlloc) X(cuMemFree) X(cuMemsetD32Async) X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) \
-    X(cuMemcpyDtoDAsync) X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostRegister) \
+    X(cuMemcpyDtoDAsync) X(cuMemcpy2DAsync) X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostRegister) \
     X(cuMemHostUnregister) \
     X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) X(cuIpcGetEventHandle) \
     X(cuIpcOpenEventHandle)
@@ -688,6 +688,26 @@ int sc_memcpy_d2d_async(void* device_dst, const void* device_src, size_t bytes, 
     CU(cuMemcpyDtoDAsync_(reinterpret_cast<CUdeviceptr>(device_dst),
                           reinterpret_cast<CUdeviceptr>(device_src), bytes,
                           reinterpret_cast<CUstream>(stream)));
+    return SC_OK;
+}
+
+int sc_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                      size_t width_bytes, size_t height, void* stream) {
+    if (!dst || !src) return fail(SC_EINVAL, "NULL pointer");
+    if (width_bytes > dst_pitch || width_bytes > src_pitch) return fail(SC_EINVAL, "row wider than its pitch");
+    NEED_CONTEXT();
+    CUDA_MEMCPY2D copy;
+    memset(&copy, 0, sizeof copy);
+    copy.srcMemoryType = CU_MEMORYTYPE_UNIFIED;          // host or device: resolved by address
+    copy.srcDevice = reinterpret_cast<CUdeviceptr>(src);
+    copy.srcPitch = src_pitch;
+    copy.dstMemoryType = CU_MEMORYTYPE_UNIFIED;
+    copy.dstDevice = reinterpret_cast<CUdeviceptr>(dst);
+    copy.dstPitch = dst_pitch;
+    copy.WidthInBytes = width_bytes;
+    copy.Height = height;
+    if (width_bytes && height)
+        CU(cuMemcpy2DAsync_(&copy, reinterpret_cast<CUstream>(stream)));
     return SC_OK;
 }
 

@@ -83,8 +83,9 @@ class FusedStencils(object):
     def _run_torch(self, stages, grid, tables):
         import torch
         stream = ctypes.c_void_p(torch.cuda.current_stream(grid.device).cuda_stream)
+        from .backend.cuda.runtime import _device_tensors
         source = grid.contiguous()
-        table_tensors = [[t.contiguous() for t in extra] for extra in tables]
+        table_tensors = [_device_tensors((source,) + extra)[1:] for extra in tables]
         steps = self._schedule(stages, tables)
         outputs = [torch.empty_like(source) for _ in range(min(2, len(steps)))]
         final = self._execute(stages, steps, source.data_ptr(), [t.data_ptr() for t in outputs],

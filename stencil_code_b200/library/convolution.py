@@ -27,6 +27,10 @@ class ConvolutionFilter(Stencil):
     def __call__(self, *args, **kwargs):
         return super(ConvolutionFilter, self).__call__(args[0], self.coefficients, **kwargs)
 
+    def iterate(self, grid, iterations, **kwargs):
+        """additive, like ``Stencil.iterate``: the coefficient vector is supplied as in ``__call__``"""
+        return super(ConvolutionFilter, self).iterate(grid, iterations, self.coefficients, **kwargs)
+
     def distance(self, x, y):
         d = tuple(x[i] - y[i] for i in range(len(x)))
         return self.neighbor_to_coefficient[d]

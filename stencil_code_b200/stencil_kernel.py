@@ -77,12 +77,14 @@ class SpecializedStencil(object):
         self.args = args
         return tuple(self._describe(arg) for arg in args)
 
-    def transform(self, arg_cfg, open_faces=(False, False), slab_ghost=None):
+    def transform(self, arg_cfg, open_faces=(False, False), slab_ghost=None, row_pitch=None):
         """Python AST -> semantic model -> CUDA plan (reference ``:278-344``).  ``open_faces``
-        marks axis-0 faces that border another slab of a multi-GPU decomposition."""
+        marks axis-0 faces that border another slab of a multi-GPU decomposition; ``row_pitch``
+        (elements) describes grid buffers with padded rows."""
         model = PythonToStencilModel().visit(self.original_tree)
         transformer = self.backend(self.args, None, self.kernel, arg_cfg=arg_cfg,
-                                   fusable_nodes=None, open_faces=open_faces, slab_ghost=slab_ghost)
+                                   fusable_nodes=None, open_faces=open_faces, slab_ghost=slab_ghost,
+                                   row_pitch=row_pitch)
         return transformer.visit(model)
 
     def finalize(self, plan):
@@ -90,14 +92,17 @@ class SpecializedStencil(object):
         from .backend.cuda.runtime import ConcreteCudaStencil
         return ConcreteCudaStencil(plan)
 
-    def specialize(self, args, open_faces=(False, False), slab_ghost=None):
+    def specialize(self, args, open_faces=(False, False), slab_ghost=None, row_pitch=None):
         if len(args) == 0:
             raise StencilException("a stencil needs at least one input grid")
-        arg_cfg = self.args_to_subconfig(args)
-        key = (arg_cfg, tuple(bool(f) for f in open_faces), slab_ghost)
+        return self.specialize_config(self.args_to_subconfig(args), open_faces, slab_ghost, row_pitch)
+
+    def specialize_config(self, arg_cfg, open_faces=(False, False), slab_ghost=None, row_pitch=None):
+        key = (arg_cfg, tuple(bool(f) for f in open_faces), slab_ghost, row_pitch)
         concrete = self._cache.get(key)
         if concrete is None:
-            concrete = self.finalize(self.transform(arg_cfg, open_faces, slab_ghost))
+            concrete = self.finalize(self.transform(arg_cfg, open_faces, slab_ghost, row_pitch))
+            concrete.origin = (self, arg_cfg)        # lets a callable ask for a sibling specialisation
             self._cache[key] = concrete
         return concrete
 

@@ -149,6 +149,16 @@ class Star(Stencil):
 def test_random_star_stencil_through_the_fused_kernel(seed, tmp_path, monkeypatch):
     """Random stencils of the shape the fused two-sweep kernel accepts (off-centre taps only in
     the middle plane, centre taps at dz = -1, 0, +1): iterate(n) vs n oracle sweeps."""
+    run_star_case(seed, (256, 388, 516), tmp_path, monkeypatch)
+
+
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_random_star_stencil_on_rows_of_odd_length(seed, tmp_path, monkeypatch):
+    """The same through iterate()'s padded-row buffers (rows that end inside a thread's quad)."""
+    run_star_case(seed, (257, 390, 515), tmp_path, monkeypatch)
+
+
+def run_star_case(seed, widths, tmp_path, monkeypatch):
     rng = random.Random(1000 + seed)
     in_plane = []
     for _ in range(rng.randint(2, 8)):
@@ -159,13 +169,18 @@ def test_random_star_stencil_through_the_fused_kernel(seed, tmp_path, monkeypatc
                                   op=rng.choice(("+", "-")))
     case = dict(seed=2000 + seed, source=source.replace("class Star", "class Fuzzed"))
     Star = load_class(case, tmp_path)
-    shape = (rng.choice((9, 14, 23)), rng.choice((18, 40, 75)), rng.choice((256, 388, 516)))
+    shape = (rng.choice((9, 14, 23)), rng.choice((18, 40, 75)), rng.choice(widths))
     boundary = rng.choice(("clamp", "zero", "copy"))
     grid = numpy.random.RandomState(seed).random_sample(shape).astype(numpy.float32)
-    monkeypatch.setenv("STENCIL_CUDA_STRATEGY", "stream")
     monkeypatch.setenv("STENCIL_CUDA_TEMPORAL", "force")      # small planes: not "worthwhile"
     stencil = Star(backend='cuda', boundary_handling=boundary)
-    assert stencil.specializer.specialize((grid,)).temporal() is not None
+    if shape[2] % 4:
+        monkeypatch.delenv("STENCIL_CUDA_STRATEGY", raising=False)    # the grid itself: one thread per point
+        concrete = stencil.specializer.specialize((grid,))._pitched_twin()
+    else:
+        monkeypatch.setenv("STENCIL_CUDA_STRATEGY", "stream")
+        concrete = stencil.specializer.specialize((grid,))
+    assert concrete is not None and concrete.temporal() is not None
     python_side = Star(backend='python', boundary_handling=boundary)
     expected = grid
     for sweeps in (1, 2, 3):
@@ -208,3 +223,30 @@ def test_random_large_windows(seed, monkeypatch):
         different = actual.view(numpy.uint32) != expected.view(numpy.uint32)
         assert not different.any(), "seed {} {} {}x{} {}: {} differ, first at {}".format(
             seed, strategy, ky, kx, boundary, int(different.sum()), tuple(numpy.argwhere(different)[0]))
+
+
+@pytest.mark.parametrize("seed", range(200, 248))
+def test_random_stencil_on_rows_of_odd_length(seed, tmp_path, monkeypatch):
+    """The random stencils of the first test on grids whose rows are no multiple of 16 bytes:
+    iterate() runs them through the streaming kernel on padded-row buffers."""
+    case = draw_case(seed)
+    if case["two_grids"]:
+        pytest.skip("padded rows are for stencils with one grid argument")
+    monkeypatch.delenv("STENCIL_CUDA_STRATEGY", raising=False)
+    Fuzzed = load_class(case, tmp_path)
+    shape = case["shape"][:-1] + (case["shape"][-1] + 1 + seed % 3,)
+    rng = numpy.random.RandomState(seed)
+    grid = rng.random_sample(shape).astype(numpy.float32)
+    tables = (case["table"],) if case["use_table"] else ()
+    python_side = Fuzzed(backend='python', boundary_handling=case["boundary"])
+    once = oracle_output(python_side, grid, *tables)
+    twice = oracle_output(python_side, once, *tables)
+    stencil = Fuzzed(backend='cuda', boundary_handling=case["boundary"])
+    twin = stencil.specializer.specialize((grid,) + tables)._pitched_twin()
+    if twin is None:
+        pytest.skip("the streaming kernel does not take this stencil")
+    for sweeps, expected in ((1, once), (2, twice)):
+        actual = stencil.iterate(grid, sweeps, *tables)
+        different = actual.view(numpy.uint32) != expected.view(numpy.uint32)
+        assert not different.any(), "seed {} {} x{}: {} differ, first at {}\n{}".format(
+            seed, case["boundary"], sweeps, int(different.sum()), tuple(numpy.argwhere(different)[0]), case["source"])

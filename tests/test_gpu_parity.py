@@ -252,3 +252,61 @@ def test_long_iterated_runs_with_programmatic_dependent_launch(strategy, shape, 
         assert_bit_identical(stencil.iterate(grid, sweeps), expected)
     monkeypatch.setenv("STENCIL_CUDA_PDL", "0")
     assert_bit_identical(stencil.iterate(grid, sweeps), expected)
+
+
+ODD_WIDTHS = [((20, 40, 513), "jacobi3d"), ((9, 70, 258), "jacobi3d"), ((12, 33, 387), "laplacian27"),
+              ((300, 1025), "odd2d"), ((130, 515), "conv5")]
+
+
+@pytest.mark.parametrize("mode", ["clamp", "zero", "copy"])
+@pytest.mark.parametrize("shape,name", ODD_WIDTHS, ids=["{}-{}".format(n, "x".join(map(str, s))) for s, n in ODD_WIDTHS])
+def test_iterate_on_rows_that_are_no_multiple_of_16_bytes(shape, name, mode, monkeypatch):
+    """TMA cannot address such grids in place; iterate() packs them into padded rows once, sweeps
+    there (streaming and fused kernels) and unpacks: same bits as the oracle applied n times."""
+    import torch
+    from cases import COEFF27, CONV5, OddWeights
+    from stencil_code_b200.library.convolution import ConvolutionFilter
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    from stencil_code_b200.library.laplacian_27pt import SpecializedLaplacian27
+    monkeypatch.delenv("STENCIL_CUDA_STRATEGY", raising=False)
+    monkeypatch.setenv("STENCIL_CUDA_TEMPORAL", "force")
+    make = {"jacobi3d": lambda backend: Jacobi3D(0.5, 0.0625, backend=backend, boundary_handling=mode),
+            "laplacian27": lambda backend: SpecializedLaplacian27(backend=backend, boundary_handling=mode),
+            "odd2d": lambda backend: OddWeights(backend=backend, boundary_handling=mode),
+            "conv5": lambda backend: ConvolutionFilter(CONV5 / 32.0, backend=backend, boundary_handling=mode)}[name]
+    tables = (COEFF27,) if name == "laplacian27" else ()
+    grid = numpy.random.RandomState(37).random_sample(shape).astype(numpy.float32)
+    stencil, python_side = make('cuda'), make('python')
+    hidden = (stencil.coefficients,) if name == "conv5" else ()   # ConvolutionFilter passes it itself
+    concrete = stencil.specializer.specialize((grid,) + tables + hidden)
+    assert concrete.plan.strategy == 'direct'                     # single calls: dense rows, no TMA
+    twin = concrete._pitched_twin()
+    assert twin is not None and twin.plan.strategy == 'stream' and twin.plan.domain.row_pitch % 4 == 0
+    expected = grid
+    for sweeps in range(1, 6):
+        expected = oracle_output(python_side, expected, *tables)
+        if sweeps in (1, 2, 5):
+            assert_bit_identical(stencil.iterate(grid, sweeps, *tables), expected)
+    tensor = torch.from_numpy(grid).cuda()
+    result = stencil.iterate(tensor, 5, *[torch.from_numpy(t).cuda() for t in tables])
+    assert result.shape == tensor.shape and result.is_contiguous()
+    assert_bit_identical(result.cpu().numpy(), expected)
+    assert_bit_identical(tensor.cpu().numpy(), grid)
+    assert_bit_identical(stencil(grid, *tables), oracle_output(python_side, grid, *tables))   # single call unchanged
+
+
+def test_padded_rows_are_not_used_where_they_do_not_apply(monkeypatch):
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    monkeypatch.delenv("STENCIL_CUDA_STRATEGY", raising=False)
+    stencil = Jacobi3D(0.5, 0.0625, backend='cuda')
+    aligned = numpy.zeros((8, 16, 64), numpy.float32)
+    assert stencil.specializer.specialize((aligned,))._pitched_twin() is None
+    double = numpy.random.RandomState(2).random_sample((8, 16, 67))
+    concrete = stencil.specializer.specialize((double,))
+    assert concrete._pitched_twin() is None
+    python_side = Jacobi3D(0.5, 0.0625, backend='python')
+    expected = oracle_output(python_side, oracle_output(python_side, double))
+    assert (stencil.iterate(double, 2).view(numpy.uint64) == expected.view(numpy.uint64)).all()
+    monkeypatch.setenv("STENCIL_CUDA_PITCHED", "0")
+    odd = numpy.random.RandomState(3).random_sample((8, 16, 67)).astype(numpy.float32)
+    assert Jacobi3D(0.5, 0.0625, backend='cuda').specializer.specialize((odd,))._pitched_twin() is None

@@ -26,6 +26,12 @@ def run(shape, n, **env):
     text = (out.stdout.strip().splitlines() or [out.stderr.strip().splitlines()[-1] if out.stderr.strip() else "?"])[-1]
     print(shape, env, "->", text, flush=True)
 
+import sys as _sys
+if len(_sys.argv) > 1 and _sys.argv[1] == "odd":
+    for shape, n in (("513x513x513", 40), ("257x1025x1025", 40), ("8193x8193", 40), ("1025x1025", 400)):
+        run(shape, n, STENCIL_CUDA_PITCHED="0")
+        run(shape, n, STENCIL_CUDA_PITCHED="1")
+    _sys.exit(0)
 for shape, n in (("32x32x32", 1000), ("64x64x64", 1000), ("128x128x128", 1000), ("192x192x192", 400), ("256x256x256", 400),
                  ("512x512x512", 100), ("512x1024x1024", 40), ("512x512", 1000), ("1024x1024", 1000),
                  ("2048x2048", 1000), ("4096x4096", 400), ("16384x16384", 20)):
