@@ -544,6 +544,26 @@ class ConcreteCudaStencil(object):
     PIPELINE_MIN_BYTES = 48 << 20      # below this a single copy-in / sweep / copy-out is used
     PIPELINE_CHUNK_BYTES = 32 << 20
 
+    @staticmethod
+    def _pipeline_bounds(lo, hi, chunks, min_planes):
+        """Axis-0 chunk boundaries of the pipelined host path: `chunks` equal parts, except that
+        the first and last ramp up / down (1/8, 1/4, 1/2 of a part) -- nothing overlaps the first
+        copy-in and the last copy-out, so they should be short."""
+        part = max(1, (hi - lo) // max(1, chunks))
+        ramp = [size for size in (part // 8, part // 4, part // 2) if size >= max(1, min_planes)]
+        sizes = list(ramp)
+        middle = (hi - lo) - 2 * sum(ramp)
+        if middle < part:
+            sizes, ramp, middle = [], [], hi - lo
+        count = max(1, middle // part)
+        sizes += [middle // count + (1 if k < middle % count else 0) for k in range(count)]
+        sizes += ramp[::-1]
+        bounds = [lo]
+        for size in sizes:
+            bounds.append(bounds[-1] + size)
+        assert bounds[-1] == hi
+        return bounds
+
     def _call_numpy(self, args, out):
         """Host arrays in, host array out.  Large grids are pipelined in axis-0 chunks over three
         streams -- copy-in of chunk i+1, sweep of chunk i and copy-out of chunk i-1 overlap, so a
@@ -578,8 +598,12 @@ class ConcreteCudaStencil(object):
                                               result.nbytes, compute))
             device.synchronize(compute)
         else:
-            bounds = [lo + (hi - lo) * k // chunks for k in range(chunks + 1)]
-            landed = [device.event() for _ in range(chunks)]
+            bounds = self._pipeline_bounds(lo, hi, chunks, 4 * ghost)
+            chunks = len(bounds) - 1
+            # head[k]: the first `ghost` planes of chunk k are on the device -- all that the sweep
+            # of chunk k-1 needs from it; landed: everything is
+            head = [device.event() for _ in range(chunks)]
+            landed = [device.event()]
             swept = [device.event() for _ in range(chunks)]
             # make sure earlier work on the compute stream (a previous call) is not overtaken
             fence = device.event()
@@ -589,15 +613,20 @@ class ConcreteCudaStencil(object):
                 check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(array.ctypes.data),
                                                   array.nbytes, copy_in))
             for k in range(chunks):
-                offset = bounds[k] * plane_bytes
-                size = (bounds[k + 1] - bounds[k]) * plane_bytes
-                check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffers[0].ptr + offset),
-                                                  ctypes.c_void_p(grid.ctypes.data + offset), size, copy_in))
-                check(library.sc_event_record(landed[k], copy_in))
+                split = min(bounds[k] + max(ghost, 1), bounds[k + 1])
+                for begin, end, event in ((bounds[k], split, head[k]), (split, bounds[k + 1], None)):
+                    if end > begin:
+                        check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffers[0].ptr + begin * plane_bytes),
+                                                          ctypes.c_void_p(grid.ctypes.data + begin * plane_bytes),
+                                                          (end - begin) * plane_bytes, copy_in))
+                    if event is not None:
+                        check(library.sc_event_record(event, copy_in))
+            check(library.sc_event_record(landed[0], copy_in))
             pointers = [b.ptr for b in buffers]
             for k in range(chunks):
-                # chunk k reads ghost planes of chunk k+1 (chunks are at least 4 ghost depths thick)
-                check(library.sc_stream_wait_event(compute, landed[min(k + 1, chunks - 1)]))
+                # chunk k reads the first ghost planes of chunk k+1; the copies are in stream order,
+                # so those having landed implies that chunk k has
+                check(library.sc_stream_wait_event(compute, head[k + 1] if k + 1 < chunks else landed[0]))
                 self.launch(pointers, out_buffer.ptr, bounds[k], bounds[k + 1], stream=compute)
                 check(library.sc_event_record(swept[k], compute))
                 check(library.sc_stream_wait_event(copy_out, swept[k]))
@@ -605,6 +634,7 @@ class ConcreteCudaStencil(object):
                 size = (bounds[k + 1] - bounds[k]) * plane_bytes
                 check(library.sc_memcpy_d2h_async(ctypes.c_void_p(result.ctypes.data + offset),
                                                   ctypes.c_void_p(out_buffer.ptr + offset), size, copy_out))
+            landed = landed + head
             device.synchronize(copy_out)
             device.synchronize(compute)
             for event in landed + swept + [fence]:
