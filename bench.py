@@ -10,7 +10,7 @@ Workloads (BASELINE.json configs):
   jacobi3d      C5  Jacobi3D 2048x1024x1024 float32, clamp, slab-decomposed over N GPUs with halo
                     exchange (default at N>1; strong scaling: the grid is fixed, slabs shrink)
   simple1024    C1  SimpleKernel 3x3 Moore, 1024^2
-  conv5         C4  ConvolutionFilter 5x5, 16384^2, --boundary zero|clamp|copy|wrap
+  conv5         C4  ConvolutionFilter 5x5, 16384^2, --boundary zero|clamp|copy|wrap|periodic
   bilateral     C3  BetterBilateralFilter radius 9, 8192^2
 
 Keys: `value` = device-resident throughput (CUDA events around K launches, inputs in HBM);
@@ -251,6 +251,7 @@ def other_workloads(peak):
             ("C4 conv5 16384^2 clamp", "conv5", "clamp", 10, False),
             ("C4 conv5 16384^2 wrap (== zero, as in the reference)", "conv5", "wrap", 10, False),
             ("C4 conv5 16384^2 copy", "conv5", "copy", 10, False),
+            ("C4 conv5 16384^2 periodic (true wrap-around: an opt-in addition, point kernel)", "conv5", "periodic", 4, False),
             ("C5 jacobi3d 2048x1024x1024 clamp, single sweeps", "jacobi3d", None, 6, False),
             ("C5 jacobi3d 2048x1024x1024 clamp, iterated (two sweeps fused per HBM pass)", "jacobi3d", None, 10, True)]
     for label, name, boundary, steps, iterated in todo:

@@ -25,10 +25,11 @@ def generate(program, domain):
     for d in range(dim - 2, -1, -1):
         strides[d] = strides[d + 1] * shape[d + 1]
     clamped = program.boundary == 'clamp'
+    wrapped = program.boundary == 'periodic'
 
     def tap_text(tap):
         name = "a{}".format(tap.arg)
-        if not clamped:
+        if not (clamped or wrapped):
             flat = sum(o * s for o, s in zip(tap.offset, strides))
             if flat == 0:
                 return "{}[idx]".format(name)
@@ -38,6 +39,8 @@ def generate(program, domain):
             o = tap.offset[d]
             if o == 0:
                 coordinate = "i{}".format(d)
+            elif wrapped:
+                coordinate = "SC_WRAP(i{d} + ({o}), {n})".format(d=d, o=o, n=shape[d])
             else:
                 coordinate = "SC_CLAMP(i{d} + ({o}), {lo}, {hi})".format(
                     d=d, o=o, lo=domain.clamp_lo[d], hi=domain.clamp_hi[d])
@@ -86,7 +89,7 @@ def generate(program, domain):
     flat = " + ".join("({}){}".format(index_t, "i{}".format(d)) if strides[d] == 1
                       else "({})i{} * {}".format(index_t, d, strides[d]) for d in range(dim))
     lines.append("    const {} idx = {};".format(index_t, flat))
-    if not clamped:
+    if not (clamped or wrapped):
         tests = []
         for d in range(dim):
             lo, hi = domain.interior_lo[d], domain.interior_hi[d]

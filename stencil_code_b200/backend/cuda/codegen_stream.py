@@ -120,6 +120,8 @@ def applicable(program, domain, device_props, forced=False):
         if arg.ctype != pp.FLOAT:
             return False, "grid argument '{}' is not float32".format(arg.name)
     n_fast = program.shape[-1]
+    if program.boundary == 'periodic':
+        return False, "periodic boundaries (TMA tiles cannot wrap around the grid)"
     if domain.row_pitch % 4 != 0:
         return False, "rows of {} floats are not a multiple of 16 bytes (TMA stride rule)".format(domain.row_pitch)
     if n_fast < 32:

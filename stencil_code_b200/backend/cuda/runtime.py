@@ -587,7 +587,8 @@ class ConcreteCudaStencil(object):
         plane_bytes = grid.nbytes // max(1, grid.shape[0])
         ghost = self.program.ghost_depth[0]
         chunks = 1
-        if grid.nbytes >= self.PIPELINE_MIN_BYTES and grid.ndim >= 2:
+        if grid.nbytes >= self.PIPELINE_MIN_BYTES and grid.ndim >= 2 and self.program.boundary != 'periodic':
+            # (periodic: the first chunk reads the last planes -- everything must have landed)
             chunks = max(1, min(64, grid.nbytes // self.PIPELINE_CHUNK_BYTES, (hi - lo) // max(1, 4 * ghost)))
         if chunks <= 1:
             for array, buffer in zip(arrays, buffers):

@@ -76,7 +76,13 @@ class StencilCudaTransformer(StencilBackend):
         if self.out_ctype not in (pp.FLOAT, pp.DOUBLE):
             raise StencilException("the first argument (the grid) must be float32 or float64")
         # 'wrap' is accepted and, exactly as in the reference, behaves like 'zero'
-        boundary = {'clamp': 'clamp', 'copy': 'copy'}.get(self.kernel.boundary_handling, 'zero')
+        boundary = {'clamp': 'clamp', 'copy': 'copy', 'periodic': 'periodic'}.get(
+            self.kernel.boundary_handling, 'zero')
+        if boundary == 'periodic':
+            if any(self.open_faces):
+                raise StencilException("periodic boundaries are not available on slab decompositions")
+            if any(g > n for g, n in zip(self.kernel.ghost_depth, shape)):
+                raise StencilException("periodic boundaries need a grid at least as wide as the stencil's reach")
         args = [self.input_dict[name] for name in self.input_names]
         args[0].used_as_grid = True
         program = pp.PointProgram(self.kernel.dim, shape, self.out_ctype, args, statements,

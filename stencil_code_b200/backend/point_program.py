@@ -184,7 +184,7 @@ class PointProgram(object):
         self.args = args                  # list[ArgInfo], inputs only (output excluded)
         self.statements = statements      # list[Store | LocalAssign]
         self.ghost_depth = tuple(int(g) for g in ghost_depth)
-        self.boundary = boundary          # 'clamp' | 'zero' | 'copy'   ('wrap' arrives as 'zero')
+        self.boundary = boundary          # 'clamp' | 'zero' | 'copy' | 'periodic'   ('wrap' arrives as 'zero')
 
     @property
     def npoints(self):

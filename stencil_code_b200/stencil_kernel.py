@@ -119,7 +119,7 @@ class Stencil(object):
                     # names the reference knows; not executable in this build
                     "c": None, "omp": None, "ocl": None, "opencl": None}
 
-    boundary_handling_list = ['clamp', 'zero', 'copy', 'wrap']
+    boundary_handling_list = ['clamp', 'zero', 'copy', 'wrap', 'periodic']
     composable = True
 
     def __call__(self, *args, **kwargs):
@@ -132,7 +132,8 @@ class Stencil(object):
             class attribute of the same name
         :param boundary_handling: one of 'clamp', 'zero', 'copy', 'wrap'.  As in the reference
             (``stencil_kernel.py:509``: the flag is spelt ``is_warped == 'warp'`` and never read)
-            'wrap' behaves exactly like 'zero'.
+            'wrap' behaves exactly like 'zero'.  'periodic' (an addition) is the true wrap-around:
+            every point is computed and a neighbor index is taken modulo the grid's extent.
         :raise StencilException: on missing neighborhoods or unknown boundary handling
         """
         if neighborhoods:
@@ -162,6 +163,7 @@ class Stencil(object):
         self.is_warped = boundary_handling == 'warp'      # sic, reference :509
         self.is_copied = boundary_handling == 'copy'
         self.is_zeroed = boundary_handling == 'zero'
+        self.is_periodic = boundary_handling == 'periodic'
 
         # communicates the shape from interior_points to neighbors (clamping); not re-entrant
         self.current_shape = None
@@ -223,7 +225,7 @@ class Stencil(object):
         """Iterate the points the kernel body runs on (reference ``:581-605``): every point when
         clamping, otherwise the points at least ``ghost_depth`` away from each face.  Records
         ``x.shape`` for ``neighbors`` when clamping, so it is not re-entrant."""
-        if self.is_clamped:
+        if self.is_clamped or self.is_periodic:
             self.current_shape = x.shape
             ranges = [range(0, extent, stride) for extent in x.shape]
         else:
@@ -246,6 +248,10 @@ class Stencil(object):
             for neighbor in neighborhood:
                 yield tuple(Stencil.clamp(point[d] + neighbor[d], 0, shape[d])
                             for d in range(len(point)))
+        elif self.is_periodic and self.current_shape is not None:
+            shape = self.current_shape
+            for neighbor in neighborhood:
+                yield tuple((point[d] + neighbor[d]) % shape[d] for d in range(len(point)))
         else:
             for neighbor in neighborhood:
                 yield tuple(p + n for p, n in zip(point, neighbor))

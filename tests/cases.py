@@ -135,3 +135,14 @@ PAIR_IDS = ["{}-{}".format(case.name, mode) for case, mode in CASE_MODE_PAIRS]
 def oracle_output(stencil, *args, **kwargs):
     from oracle.cref import reference_c
     return reference_c(stencil, *args, **kwargs)
+
+
+def periodic_oracle(make, grid, *tables):
+    """Oracle for boundary_handling='periodic' (an addition; the reference's 'wrap' is 'zero'):
+    pad the grid by the ghost depth with numpy.pad(mode='wrap'), run the restated reference C in
+    'zero' mode (interior only) on the padded grid, crop.  ``make(mode)`` builds the stencil."""
+    stencil = make('zero')
+    ghost = stencil.ghost_depth
+    padded = numpy.ascontiguousarray(numpy.pad(grid, [(g, g) for g in ghost], mode='wrap'))
+    result = oracle_output(stencil, padded, *tables)
+    return numpy.ascontiguousarray(result[tuple(slice(g, g + n) for g, n in zip(ghost, grid.shape))])

@@ -246,3 +246,17 @@ def test_dependent_launch_variant_compiles_for_every_kernel_family(tmp_path):
                 path.write_bytes(data)
                 sass = subprocess.run(["cuobjdump", "-sass", str(path)], capture_output=True, text=True).stdout
                 assert ("ACQBULK" in sass and "PREEXIT" in sass) == expected     # wait / launch_dependents
+
+
+def test_host_pipeline_chunk_bounds():
+    """Chunks of the pipelined numpy path: cover [lo, hi) exactly, none thinner than four ghost
+    depths (a chunk's sweep reads ghost planes of its neighbours only), short first and last."""
+    bounds_of = runtime.ConcreteCudaStencil._pipeline_bounds
+    for lo, hi, chunks, thin in ((0, 512, 16, 4), (0, 512, 32, 4), (0, 100, 3, 4), (1, 63, 2, 8),
+                                 (0, 2048, 64, 4), (0, 16, 4, 4), (0, 7, 1, 4), (3, 40, 5, 36)):
+        bounds = bounds_of(lo, hi, chunks, thin)
+        sizes = [b - a for a, b in zip(bounds, bounds[1:])]
+        assert bounds[0] == lo and bounds[-1] == hi and all(size > 0 for size in sizes)
+        assert len(sizes) == 1 or min(sizes) >= min(thin, (hi - lo) // max(1, chunks))
+        assert sizes[0] <= max(sizes) and sizes[-1] <= max(sizes)
+    assert [b - a for a, b in zip(bounds_of(0, 512, 16, 4), bounds_of(0, 512, 16, 4)[1:])][:3] == [4, 8, 16]
