@@ -10,13 +10,17 @@ Every output element in the requested axis-0 range is written exactly once, so t
 needs no zero-fill beforehand (the reference's ``zeros`` allocation, ``stencil_kernel.py:412-416``,
 is folded into the kernel: the accumulator starts at 0).
 """
+import os
+
 from ...stencil_exception import StencilException
 from .codegen_common import PROLOGUE, ctype_zero, emit_statements
 
 BLOCK_THREADS = 256
 
 
-def generate(program, domain):
+def generate(program, domain, config=None):
+    if config is not None and config.get('kind') == 'tiled':
+        return generate_tiled(program, domain, config)
     dim = program.dim
     shape = program.shape
     big = program.npoints >= 2 ** 31 - 2 ** 20
@@ -112,7 +116,164 @@ def generate(program, domain):
     return "\n".join(lines) + "\n"
 
 
-def launch_geometry(program, a0_begin, a0_end):
+# ---- rank 2 / rank 3: a column of points per thread ---------------------------------------------
+TILE_THREADS = 128
+
+
+def _tag(v):
+    return "m{}".format(-v) if v < 0 else str(v)
+
+
+def direct_config(program, domain):
+    """How ``stencil_direct`` walks the grid.  'flat': one thread per point over the flattened
+    range (any rank).  'tiled' (rank 2 and 3, rows of at least 96 elements): a thread owns RZ x RY
+    points that share their last-axis index; a tap value needed by several of them is loaded once.
+    The flat kernel is bound by L2 -> L1 traffic (every row is fetched once per tap row that
+    touches it: 5 times for the 7-point star); the tiled one fetches 20 rows for 8 points."""
+    dim = program.dim
+    if dim not in (2, 3) or program.shape[-1] < 96 or os.environ.get("STENCIL_CUDA_DIRECT", "tiled") == "flat":
+        return dict(kind='flat')
+    reach = max(program.ghost_depth)
+    taps = {(t.arg,) + tuple(t.offset) for t in program.taps()}
+    wide = 2 if program.out_ctype == 'double' else 1
+    for RY, RZ in ((4, 2), (4, 1), (2, 1)):
+        if dim == 2:
+            RZ = 1
+        unique = {(arg, rz + (o[0] if dim == 3 else 0), ry + o[-2], o[-1])
+                  for (arg, *o) in taps for rz in range(RZ) for ry in range(RY)}
+        rows = program.shape[-2]
+        planes = program.shape[0] if dim == 3 else 1
+        if program.boundary == 'periodic' and (rows < 2 * (RY + reach) or (dim == 3 and planes < 2 * (RZ + reach))):
+            continue                      # SC_WRAP takes indices in [-n, 2n) only
+        if len(unique) * wide <= 56 and -(-rows // RY) <= 65535 and -(-planes // RZ) <= 65535:
+            return dict(kind='tiled', RY=RY, RZ=RZ)
+    return dict(kind='flat')
+
+
+def generate_tiled(program, domain, config):
+    dim, shape = program.dim, program.shape
+    RY, RZ = config['RY'], config['RZ']
+    big = program.npoints >= 2 ** 31 - 2 ** 20
+    index_t = 'i64' if big else 'int'
+    n_last, n_rows = shape[-1], shape[-2]
+    s_row = n_last
+    s_plane = n_last * n_rows
+    mode = program.boundary
+    row_axis, col_axis = dim - 2, dim - 1
+
+    def coordinate(axis, text):
+        if mode == 'periodic':
+            return "SC_WRAP({}, {})".format(text, shape[axis])
+        if mode == 'clamp':
+            return "SC_CLAMP({}, {}, {})".format(text, domain.clamp_lo[axis], domain.clamp_hi[axis])
+        return "SC_CLAMP({}, 0, {})".format(text, shape[axis] - 1)      # address safety only
+
+    taps = sorted({(t.arg,) + tuple(t.offset) for t in program.taps()})
+    if mode == 'copy':
+        taps = sorted(set(taps) | {(0,) + (0,) * dim})
+    unique = sorted({(arg, rz + (o[0] if dim == 3 else 0), ry + o[-2], o[-1])
+                     for (arg, *o) in taps for rz in range(RZ) for ry in range(RY)})
+    ctype_of = {arg.index: arg.ctype for arg in program.args}
+
+    params = []
+    for arg in program.args:
+        params.append("const {}* __restrict__ a{}".format(arg.ctype, arg.index))
+    params += ["{}* __restrict__ out".format(program.out_ctype), "{}* __restrict__ out_peer".format(program.out_ctype),
+               "i64 peer_shift", "int a0_begin", "int a0_end"]
+    lines = [PROLOGUE]
+    lines.append("// direct strategy, tiled: {} x {} points per thread | grid {} boundary {}".format(RZ, RY, shape, mode))
+    lines.append('extern "C" __global__ void __launch_bounds__({})'.format(TILE_THREADS))
+    lines.append("stencil_direct({})".format(", ".join(params)))
+    lines.append("{")
+    lines.append("    pdl_launch_dependents();")
+    lines.append("    pdl_wait();")
+    lines.append("    const int ix = blockIdx.x * {} + threadIdx.x;".format(TILE_THREADS))
+    lines.append("    if (ix >= {}) return;".format(n_last))
+    if dim == 3:
+        lines.append("    const int iy = blockIdx.y * {};".format(RY))
+        lines.append("    const int iz = a0_begin + blockIdx.z * {};".format(RZ))
+        lines.append("    const int row_end = {}, plane_end = a0_end;".format(n_rows))
+    else:
+        lines.append("    const int iy = a0_begin + blockIdx.y * {};".format(RY))
+        lines.append("    const int row_end = a0_end;")
+    for c in sorted({u[3] for u in unique}):
+        lines.append("    const int x_{} = {};".format(_tag(c), "ix" if c == 0 else coordinate(col_axis, "ix + ({})".format(c))))
+    for c in sorted({u[2] for u in unique}):
+        lines.append("    const {t} y_{n} = ({t}){e} * {s};".format(
+            t=index_t, n=_tag(c), e=coordinate(row_axis, "iy + ({})".format(c)), s=s_row))
+    if dim == 3:
+        for c in sorted({u[1] for u in unique}):
+            lines.append("    const {t} z_{n} = ({t}){e} * {s}{ll};".format(
+                t=index_t, n=_tag(c), e=coordinate(0, "iz + ({})".format(c)), s=s_plane, ll='LL' if big else ''))
+
+    def value_name(arg, cz, cy, cx):
+        return "v{}_{}_{}_{}".format(arg, _tag(cz), _tag(cy), _tag(cx))
+    for (arg, cz, cy, cx) in unique:
+        base = "y_{}".format(_tag(cy)) + (" + z_{}".format(_tag(cz)) if dim == 3 else "")
+        lines.append("    const {} {} = a{}[{} + x_{}];".format(ctype_of[arg], value_name(arg, cz, cy, cx), arg, base, _tag(cx)))
+
+    def table_text(ref, index_text):
+        return "a{}[{}]".format(ref.arg, index_text)
+
+    halo_modes = mode in ('zero', 'copy')
+    for rz in range(RZ):
+        for ry in range(RY):
+            valid = ["iy + {} < row_end".format(ry)]
+            if dim == 3:
+                valid.append("iz + {} < plane_end".format(rz))
+            lines.append("    if ({}) {{".format(" && ".join(valid)))
+            if dim == 3:
+                lines.append("        const {t} idx = ({t})(iz + {rz}) * {sp}{ll} + ({t})(iy + {ry}) * {sr} + ix;".format(
+                    t=index_t, rz=rz, ry=ry, sp=s_plane, sr=s_row, ll='LL' if big else ''))
+            else:
+                lines.append("        const {t} idx = ({t})(iy + {ry}) * {sr} + ix;".format(t=index_t, ry=ry, sr=s_row))
+            lines.append("        {} acc = {};".format(program.out_ctype, ctype_zero(program.out_ctype)))
+            tests = []
+            if halo_modes:
+                coords = {col_axis: "ix", row_axis: "iy + {}".format(ry)}
+                if dim == 3:
+                    coords[0] = "iz + {}".format(rz)
+                for d in range(dim):
+                    lo, hi = domain.interior_lo[d], domain.interior_hi[d]
+                    if lo > 0:
+                        tests.append("{} < {}".format(coords[d], lo))
+                    if hi < shape[d]:
+                        tests.append("{} >= {}".format(coords[d], hi))
+
+            def tap_text(tap, rz=rz, ry=ry):
+                o = tuple(tap.offset)
+                return value_name(tap.arg, rz + (o[0] if dim == 3 else 0), ry + o[-2], o[-1])
+            body = emit_statements(program, tap_text, table_text, indent="            ")
+            if tests:
+                halo_value = ctype_zero(program.out_ctype)
+                if mode == 'copy':
+                    halo_value = value_name(0, rz, ry, 0)
+                    if program.args[0].ctype != program.out_ctype:
+                        halo_value = "({}){}".format(program.out_ctype, halo_value)
+                lines.append("        if ({}) acc = {};".format(" || ".join(tests), halo_value))
+                lines.append("        else {")
+                lines.extend(body)
+                lines.append("        }")
+            else:
+                lines.append("        {")
+                lines.extend(body)
+                lines.append("        }")
+            lines.append("        out[idx] = acc;")
+            if domain.is_slab:
+                lines.append("        if (out_peer) out_peer[idx + peer_shift] = acc;")
+            lines.append("    }")
+    lines.append("}")
+    return "\n".join(lines) + "\n"
+
+
+def launch_geometry(program, a0_begin, a0_end, config=None):
+    if config is not None and config.get('kind') == 'tiled':
+        tiles_x = -(-program.shape[-1] // TILE_THREADS)
+        if program.dim == 3:
+            grid = (tiles_x, -(-program.shape[1] // config['RY']), max(1, -(-(a0_end - a0_begin) // config['RZ'])))
+        else:
+            grid = (tiles_x, max(1, -(-(a0_end - a0_begin) // config['RY'])), 1)
+        return grid, (TILE_THREADS, 1, 1)
     per0 = 1
     for s in program.shape[1:]:
         per0 *= s

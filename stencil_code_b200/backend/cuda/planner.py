@@ -55,14 +55,15 @@ def plan(program, domain, device_props=None, forced_strategy=None, options=()):
         return codegen_stream.make_plan(program, domain, device_props, options)
     if strategy != 'direct':
         raise StencilException("unknown strategy '{}'".format(strategy))
-    source = codegen_direct.generate(program, domain)
+    config = codegen_direct.direct_config(program, domain)
+    source = codegen_direct.generate(program, domain, config)
 
     def geometry(a0_begin, a0_end):
-        grid, block = codegen_direct.launch_geometry(program, a0_begin, a0_end)
+        grid, block = codegen_direct.launch_geometry(program, a0_begin, a0_end, config)
         return Launch(grid, block)
 
     return CudaPlan(program, domain, 'direct', source, 'stencil_direct', options, geometry,
-                    notes={'why': reason})
+                    notes={'why': reason, 'config': config})
 
 
 def halo_slabs(shape, ghost_depth):

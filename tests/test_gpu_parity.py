@@ -310,3 +310,32 @@ def test_padded_rows_are_not_used_where_they_do_not_apply(monkeypatch):
     monkeypatch.setenv("STENCIL_CUDA_PITCHED", "0")
     odd = numpy.random.RandomState(3).random_sample((8, 16, 67)).astype(numpy.float32)
     assert Jacobi3D(0.5, 0.0625, backend='cuda').specializer.specialize((odd,))._pitched_twin() is None
+
+
+@pytest.mark.parametrize("mode", ["clamp", "zero", "copy", "periodic"])
+def test_point_kernel_flat_and_tiled_forms_agree(mode, monkeypatch):
+    """'direct' walks rank-2/3 grids with RZ x RY points per thread (shared loads) and everything
+    else with one point per thread; both forms against the oracle on the same grids, float32 and
+    float64, ragged tile edges (rows and planes that are no multiples of RY / RZ)."""
+    from cases import OddWeights, WideStar3D, periodic_oracle
+    from stencil_code_b200.library.laplacian_27pt import SpecializedLaplacian27
+    from cases import COEFF27
+    monkeypatch.setenv("STENCIL_CUDA_STRATEGY", "direct")
+    cases = [(lambda backend, m: WideStar3D(backend=backend, boundary_handling=m), (11, 30, 132), (), numpy.float32),
+             (lambda backend, m: SpecializedLaplacian27(backend=backend, boundary_handling=m), (7, 13, 100), (COEFF27,), numpy.float32),
+             (lambda backend, m: OddWeights(backend=backend, boundary_handling=m), (51, 261), (), numpy.float32),
+             (lambda backend, m: WideStar3D(backend=backend, boundary_handling=m), (9, 10, 97), (), numpy.float64)]
+    for make, shape, tables, dtype in cases:
+        grid = numpy.random.RandomState(41).random_sample(shape).astype(dtype)
+        if mode == "periodic":
+            expected = periodic_oracle(lambda m: make('python', m), grid, *tables)
+        else:
+            expected = oracle_output(make('python', mode), grid, *tables)
+        view = numpy.uint32 if dtype == numpy.float32 else numpy.uint64
+        for form in ("tiled", "flat"):
+            monkeypatch.setenv("STENCIL_CUDA_DIRECT", form)
+            stencil = make('cuda', mode)
+            concrete = stencil.specializer.specialize((grid,) + tables)
+            assert concrete.plan.notes['config']['kind'] == form
+            actual = stencil(grid, *tables)
+            assert (actual.view(view) == expected.view(view)).all(), (form, shape, mode)

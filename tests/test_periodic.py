@@ -55,7 +55,12 @@ def test_periodic_takes_the_point_kernel_and_wraps_indices(monkeypatch):
     from stencil_code_b200.backend.cuda import runtime
     monkeypatch.delenv("STENCIL_CUDA_STRATEGY", raising=False)
     plan = make_plan(LaplacianKernel(boundary_handling='periodic'), [((64, 128, 256), numpy.float32)])
-    assert plan.strategy == 'direct' and "SC_WRAP(i0 + (1), 64)" in plan.source and "SC_CLAMP(i" not in plan.source
+    assert plan.strategy == 'direct' and "SC_WRAP(iz + (1), 64)" in plan.source and "SC_CLAMP(i" not in plan.source
+    monkeypatch.setenv("STENCIL_CUDA_DIRECT", "flat")          # the one-point-per-thread form of the same kernel
+    flat = make_plan(LaplacianKernel(boundary_handling='periodic'), [((64, 128, 256), numpy.float32)])
+    assert "SC_WRAP(i0 + (1), 64)" in flat.source
+    runtime.compile_source(flat.source, "periodic_flat.cu", flat.options)
+    monkeypatch.delenv("STENCIL_CUDA_DIRECT")
     runtime.compile_source(plan.source, "periodic.cu", plan.options)
     with pytest.raises(StencilException):
         make_plan(LaplacianKernel(boundary_handling='periodic'), [((64, 128, 256), numpy.float32)], 'stream')
