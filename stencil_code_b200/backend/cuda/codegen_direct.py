@@ -136,7 +136,14 @@ def direct_config(program, domain):
     reach = max(program.ghost_depth)
     taps = {(t.arg,) + tuple(t.offset) for t in program.taps()}
     wide = 2 if program.out_ctype == 'double' else 1
-    for RY, RZ in ((4, 2), (4, 1), (2, 1)):
+    # measured on B200 (GStencil/s): 7-point (8,2) 561, (4,4) 560, (4,2) 536, (2,4) 516, (8,1) 460;
+    # 27-point (4,2) 235, (8,1) 217, (4,1) 205; 5x5 (8,1) 305, (4,1) 258, (2,1) 197
+    candidates = ((8, 2), (4, 2), (8, 1), (4, 1), (2, 1))
+    forced = os.environ.get("STENCIL_CUDA_DIRECT_TILE")              # tuning knob: "RY,RZ"
+    if forced:
+        candidates = (tuple(int(v) for v in forced.split(",")),)
+        wide = 0
+    for RY, RZ in candidates:
         if dim == 2:
             RZ = 1
         unique = {(arg, rz + (o[0] if dim == 3 else 0), ry + o[-2], o[-1])
@@ -145,7 +152,7 @@ def direct_config(program, domain):
         planes = program.shape[0] if dim == 3 else 1
         if program.boundary == 'periodic' and (rows < 2 * (RY + reach) or (dim == 3 and planes < 2 * (RZ + reach))):
             continue                      # SC_WRAP takes indices in [-n, 2n) only
-        if len(unique) * wide <= 56 and -(-rows // RY) <= 65535 and -(-planes // RZ) <= 65535:
+        if len(unique) * wide <= 72 and -(-rows // RY) <= 65535 and -(-planes // RZ) <= 65535:
             return dict(kind='tiled', RY=RY, RZ=RZ)
     return dict(kind='flat')
 

@@ -26,6 +26,17 @@ ms = start.elapsed_time(stop) / 5
 concrete = stencil.specializer.specialize((grid,) + tables + ((stencil.coefficients,) if kind == "conv5" else ()))
 print("{:.3f} ms {:.0f} GStencil/s {} {}".format(ms, numpy.prod(shape) / ms / 1e6, concrete.plan.strategy, concrete.plan.notes.get('config')))
 '''
+if len(sys.argv) > 1 and sys.argv[1] == "tiles":
+    for kind, mode, dtype, tiles in (("jacobi3d", "clamp", "float32", ("4,2", "8,2", "4,4", "8,1", "2,2", "2,4")),
+                                     ("jacobi3d", "clamp", "float64", ("4,1", "4,2", "8,1", "2,2")),
+                                     ("conv5", "clamp", "float32", ("4,1", "8,1", "2,1")),
+                                     ("lap27", "clamp", "float32", ("4,1", "4,2", "2,2", "8,1"))):
+        for tile in tiles:
+            env = dict(os.environ, PYTHONPATH=".", STENCIL_CUDA_DIRECT_TILE=tile)
+            out = subprocess.run([sys.executable, "-c", CHILD, kind, mode, dtype], env=env, capture_output=True, text=True)
+            text = (out.stdout.strip().splitlines() or [(out.stderr.strip().splitlines() or ["?"])[-1]])[-1]
+            print(kind, mode, dtype, tile, "->", text, flush=True)
+    sys.exit(0)
 for kind, mode, dtype in (("jacobi3d", "clamp", "float32"), ("jacobi3d", "zero", "float32"), ("jacobi3d", "periodic", "float32"),
                           ("jacobi3d", "clamp", "float64"), ("lap27", "clamp", "float32"), ("conv5", "clamp", "float32"),
                           ("conv5", "periodic", "float32")):
