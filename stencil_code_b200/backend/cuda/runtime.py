@@ -524,15 +524,18 @@ class ConcreteCudaStencil(object):
             self.last_duration = time.perf_counter() - begin
         return result
 
-    def _call_torch(self, args, out):
-        import torch
-        grid = args[0]
+    def _require_device_tensor(self, grid):
         if not grid.is_cuda:
             raise StencilException("torch tensors must live on a CUDA device (numpy arrays are "
                                    "copied for you)")
         if grid.device.index != self.device.index:
             raise StencilException("tensor is on cuda:{} but the stencil was specialised on cuda:{}"
                                    .format(grid.device.index, self.device.index))
+
+    def _call_torch(self, args, out):
+        import torch
+        grid = args[0]
+        self._require_device_tensor(grid)
         tensors = _device_tensors(args)
         result = torch.empty_like(tensors[0]) if out is None else out
         if not result.is_contiguous():
@@ -815,6 +818,8 @@ class ConcreteCudaStencil(object):
         self._check_args(args)
         library = load_library()
         device = self.device
+        if _is_torch_tensor(grid):
+            self._require_device_tensor(grid)
         twin = self._pitched_twin() if iterations >= 1 else None
         if twin is not None:
             return self._iterate_pitched(twin, args, iterations)

@@ -48,6 +48,7 @@ class FusedStencils(object):
         for concrete, extra in zip(stages, tables):
             concrete._check_args((grid,) + extra)
         if runtime._is_torch_tensor(grid):
+            stages[0]._require_device_tensor(grid)
             return self._run_torch(stages, grid, tables)
         return self._run_numpy(stages, grid, tables)
 

@@ -164,6 +164,17 @@ def test_wrong_shape_raises_type_error():
         concrete(numpy.zeros((8, 8, 9), numpy.float32))
 
 
+def test_host_side_torch_tensors_are_refused_everywhere():
+    import torch
+    from stencil_code_b200 import StencilException, fuse
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    stencil = LaplacianKernel()
+    host = torch.zeros((8, 8, 8))
+    for call in (lambda: stencil(host), lambda: stencil.iterate(host, 2), lambda: fuse(stencil, stencil)(host)):
+        with pytest.raises(StencilException, match="CUDA device"):
+            call()
+
+
 def test_product_never_imports_the_oracle():
     import sys
     import subprocess
