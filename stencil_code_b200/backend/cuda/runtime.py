@@ -507,8 +507,13 @@ class ConcreteCudaStencil(object):
     # -- the call --------------------------------------------------------------------------------
     def __call__(self, *args, **kwargs):
         out = kwargs.pop("out", None)
+        iterations = kwargs.pop("iterations", None)
         if kwargs:
             raise StencilException("unexpected keyword arguments {}".format(sorted(kwargs)))
+        if iterations is not None:                      # additive: stencil(grid, iterations=n)
+            if out is not None:
+                raise StencilException("out= and iterations= cannot be combined")
+            return self.iterate(args[0], int(iterations), *args[1:])
         self._check_args(args)
         timed = os.environ.get("STENCIL_CUDA_TIMING", "0") not in ("0", "")
         if timed:

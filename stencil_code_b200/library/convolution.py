@@ -25,6 +25,8 @@ class ConvolutionFilter(Stencil):
             neighborhoods=[neighbors], backend=backend, boundary_handling=boundary_handling)
 
     def __call__(self, *args, **kwargs):
+        if kwargs.get('iterations') is not None:
+            return self.iterate(args[0], int(kwargs.pop('iterations')), **kwargs)
         return super(ConvolutionFilter, self).__call__(args[0], self.coefficients, **kwargs)
 
     def iterate(self, grid, iterations, **kwargs):

@@ -123,6 +123,9 @@ class Stencil(object):
     composable = True
 
     def __call__(self, *args, **kwargs):
+        iterations = kwargs.pop('iterations', None)          # additive: stencil(grid, iterations=n)
+        if iterations is not None:
+            return self.iterate(args[0], int(iterations), *args[1:], **kwargs)
         return self.specializer(*args, **kwargs)
 
     def __init__(self, backend='cuda', neighborhoods=None, boundary_handling='clamp', **kwargs):

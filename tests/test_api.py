@@ -122,3 +122,18 @@ def test_halo_enumerator():
             halo = list(kernel.halo_points(numpy.zeros(shape)))
             assert len(halo) == len(set(halo)) == product(shape) - len(interior)
             assert not interior & set(halo) and interior | set(halo) == everything
+
+
+def test_iterations_keyword_and_iterate_on_the_python_backend():
+    """additive API: stencil(grid, iterations=n) == stencil.iterate(grid, n) == n chained calls"""
+    import numpy
+    from stencil_code_b200.library.convolution import ConvolutionFilter
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    grid = numpy.random.RandomState(9).random_sample((5, 6, 7)).astype(numpy.float32)
+    stencil = Jacobi3D(0.5, 0.0625, backend='python')
+    chained = stencil(stencil(stencil(grid)))
+    assert (stencil(grid, iterations=3) == chained).all() and (stencil.iterate(grid, 3) == chained).all()
+    assert (stencil.iterate(grid, 0) == grid).all()
+    flat = numpy.random.RandomState(9).random_sample((9, 11)).astype(numpy.float32)
+    conv = ConvolutionFilter(numpy.array([[0, 0.25, 0], [0.25, 0, 0.25], [0, 0.25, 0]]), backend='python')
+    assert (conv(flat, iterations=2) == conv(conv(flat))).all() and (conv.iterate(flat, 2) == conv(conv(flat))).all()

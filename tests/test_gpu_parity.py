@@ -148,6 +148,9 @@ def test_iterate_equals_repeated_calls():
     for _ in range(5):
         looped = stencil(looped)
     assert_bit_identical(stencil.iterate(grid, 5), looped)
+    assert_bit_identical(stencil(grid, iterations=5), looped)         # the keyword form of the same
+    concrete = stencil.specializer.specialize((grid,))
+    assert_bit_identical(concrete(grid, iterations=5), looped)
     reference = grid
     python_side = Jacobi3D(1.0, 0.25, backend='python')
     for _ in range(5):
