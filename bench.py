@@ -425,8 +425,25 @@ def main():
 
     if args.gpus > 1 or world > 1:
         from stencil_code_b200.backend.cuda import multi_gpu_bench
-        line = multi_gpu_bench.run(args, make_workload(args.workload, args.boundary, "cuda"))
+        workload = make_workload(args.workload, args.boundary, "cuda")
+        one_gpu = None
+        if rank == 0 and not args.quick:
+            # the same workload on rank 0's GPU alone, whole grid, same kernels: the denominator of
+            # a parallel efficiency (the default N=1 line is another workload, C2)
+            try:
+                alone = device_sweeps(workload, 10, 3, iterated=True)
+                from stencil_code_b200.backend.cuda import runtime
+                runtime.Device.get(int(os.environ.get("LOCAL_RANK", "0"))).trim()     # hand the 16 GiB back
+                one_gpu = {"value": alone["gstencil_s"], "unit": "GStencil/s", "ms_per_step": alone["ms_per_sweep"],
+                           "strategy": alone["strategy"],
+                           "what": "this workload, undecomposed, on one GPU of this box, iterated, 10 sweeps "
+                                   "after 4 of warm-up, timed with CUDA events before the decomposed run"}
+            except Exception as error:       # must not lose the multi-GPU line
+                one_gpu = {"error": str(error)[:200]}
+        line = multi_gpu_bench.run(args, workload)
         if line is not None:
+            if one_gpu is not None:
+                line["one_gpu_same_workload"] = one_gpu
             print(json.dumps(line))
         return
     print(json.dumps(run_single_gpu(args, make_workload(args.workload, args.boundary, "cuda"))))
