@@ -414,7 +414,8 @@ def main():
         base = cpu_reference_run(workload, steps=args.steps, warmup=args.warmup)
         line = {"impl": "reference", "metric": "GStencil/s", "value": base["value"], "unit": "GStencil/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": base["ms_per_sweep"], "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": base["ms_per_sweep"], "higher_is_better": True,
+                "scaling": "weak" if args.gpus == 1 else "strong",      # as the cuda arm labels the same N
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic (numpy RandomState(1) uniform)",
                 "config": {"workload": workload["label"], "cpu_grid": list(workload["cpu_shape"])},
                 "cpu_baseline": base,
