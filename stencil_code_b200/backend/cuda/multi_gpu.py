@@ -17,10 +17,14 @@ neighbours' flags reached the previous sweep number.  Interior planes never read
 a neighbour can never overwrite ghosts that are still being read (see ``iterate``).
 
 ``torch.distributed`` is used for the plumbing only: exchanging CUDA IPC handles, barriers and the
-final reductions.  Results are bit-identical to the single-GPU sweep: the per-point arithmetic is
+final reductions.  ``STENCIL_CUDA_EXCHANGE=nccl`` selects the conventional alternative -- the
+boundary launches store locally only and the ghost planes travel by grouped NCCL send/recv on the
+edge stream, still overlapped with the interior launch -- kept as the baseline the peer stores are
+measured against (and for boxes without peer access between the GPUs).  Results are bit-identical to the single-GPU sweep: the per-point arithmetic is
 the same generated code, only ``Domain`` (open faces) differs.
 """
 import ctypes
+import os
 
 import numpy
 
@@ -151,8 +155,13 @@ class SlabStencil(object):
         self.interior_done = self.device.new_event()
         self._events_armed = False
         self.peers = {}
-        if slab.ghosted:
+        self.exchange = os.environ.get("STENCIL_CUDA_EXCHANGE", "peer") if slab.ghosted else "none"
+        if self.exchange not in ("peer", "nccl", "none"):
+            raise StencilException("STENCIL_CUDA_EXCHANGE must be 'peer' or 'nccl'")
+        if self.exchange == "peer":
             self._open_peers()
+        elif self.exchange == "nccl":
+            self._prepare_nccl()
 
     # -- setup -----------------------------------------------------------------------------------
     def _handle(self, pointer):
@@ -177,7 +186,57 @@ class SlabStencil(object):
                                          "flags": self._open(info["flags"])}
         self.dist.barrier()
 
+    def _prepare_nccl(self):
+        """torch views of the planes each buffer sends and receives, and the edge stream as a torch
+        stream: the send/recv group is enqueued there, between the boundary launches and the
+        event the next sweep's interior launch waits for."""
+        import torch
+        slab = self.slab
+        plane = slab.plane_elems
+
+        class _Planes(object):
+            """zero-copy view of device memory for torch.as_tensor"""
+            def __init__(self, pointer, count):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (pointer, False),
+                                                 "version": 2}
+        device = torch.device("cuda", self.device.index)
+
+        def view(buffer, first, last):
+            return torch.as_tensor(_Planes(buffer.ptr + first * plane * 4, (last - first) * plane), device=device)
+        lo, hi = slab.first_real, slab.first_real + slab.planes
+        self._nccl_views = []
+        for buffer in self.buffers:
+            views = {}
+            if slab.open_lo:
+                views["up"] = (view(buffer, lo, lo + slab.g), view(buffer, 0, slab.g))                  # send, recv
+            if slab.open_hi:
+                views["down"] = (view(buffer, hi - slab.g, hi), view(buffer, hi, hi + slab.g))
+            self._nccl_views.append(views)
+        self._edge_torch_stream = torch.cuda.ExternalStream(self.edge_stream.value if hasattr(self.edge_stream, "value")
+                                                            else int(self.edge_stream), device=device)
+        for neighbour in (slab.rank - 1, slab.rank + 1):
+            if 0 <= neighbour < slab.world:
+                self.peers[neighbour] = {"nccl": True}
+
+    def _exchange_nccl(self, target_index):
+        import torch
+        dist, slab = self.dist, self.slab
+        views = self._nccl_views[target_index]
+        operations = []
+        if "up" in views:
+            send, receive = views["up"]
+            operations += [dist.P2POp(dist.isend, send, slab.rank - 1), dist.P2POp(dist.irecv, receive, slab.rank - 1)]
+        if "down" in views:
+            send, receive = views["down"]
+            operations += [dist.P2POp(dist.isend, send, slab.rank + 1), dist.P2POp(dist.irecv, receive, slab.rank + 1)]
+        with torch.cuda.stream(self._edge_torch_stream):
+            for work in dist.batch_isend_irecv(operations):
+                work.wait()                      # stream-ordered: the edge stream waits, not the host
+
     def close(self):
+        if self.exchange != "peer":
+            self.peers = {}
+            return
         for peer in self.peers.values():
             for pointer in peer["buffers"] + [peer["flags"]]:
                 self.library.sc_ipc_close_mem_handle(ctypes.c_void_p(pointer))
@@ -300,21 +359,30 @@ class SlabStencil(object):
                 if number > 1 or self._events_armed:
                     runtime.check(library.sc_stream_wait_event(edge, self.interior_done))
                     runtime.check(library.sc_stream_wait_event(main, self.edge_done))
-                if number > 1:
+                if number > 1 and self.exchange == "peer":
                     # flags: [0] written by the upper neighbour, [1] by the lower one
                     if up:
                         runtime.check(library.sc_stream_wait_value32(edge, ctypes.c_void_p(self.flags.ptr), number - 1))
                     if down:
                         runtime.check(library.sc_stream_wait_value32(edge, ctypes.c_void_p(self.flags.ptr + 4), number - 1))
-                if up:
-                    # my first g real planes become the upper neighbour's lower ghost planes
-                    run(top[0], top[1], edge, up["buffers"][target_index], slab.counts[slab.rank - 1] * plane)
-                if down:
-                    run(bottom[0], bottom[1], edge, down["buffers"][target_index], -slab.planes * plane)
-                runtime.launch(self.device.utils(), "sc_signal", signal_geometry,
-                               [ctypes.c_void_p(up["flags"] + 4 if up else 0),
-                                ctypes.c_void_p(down["flags"] if down else 0),
-                                ctypes.c_uint32(number)], edge)
+                if self.exchange == "nccl":
+                    # boundary planes land locally; a grouped send/recv carries them into the
+                    # neighbours' ghost planes of the same buffer (ordering between ranks is NCCL's)
+                    if up:
+                        run(top[0], top[1], edge)
+                    if down:
+                        run(bottom[0], bottom[1], edge)
+                    self._exchange_nccl(target_index)
+                else:
+                    if up:
+                        # my first g real planes become the upper neighbour's lower ghost planes
+                        run(top[0], top[1], edge, up["buffers"][target_index], slab.counts[slab.rank - 1] * plane)
+                    if down:
+                        run(bottom[0], bottom[1], edge, down["buffers"][target_index], -slab.planes * plane)
+                    runtime.launch(self.device.utils(), "sc_signal", signal_geometry,
+                                   [ctypes.c_void_p(up["flags"] + 4 if up else 0),
+                                    ctypes.c_void_p(down["flags"] if down else 0),
+                                    ctypes.c_uint32(number)], edge)
                 runtime.check(library.sc_event_record(self.edge_done, edge))
             run(interior[0], interior[1], main)
             if exchanging:

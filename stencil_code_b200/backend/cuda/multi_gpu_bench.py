@@ -88,9 +88,11 @@ def run(args, workload):
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (counter-based uniform, generated on device)",
-            "config": {"workload": workload["label"] + ", slab-decomposed along axis 0, {} planes per GPU, "
-                       "ghost planes written by the neighbour's kernel through NVLink peer memory".format(
-                           decomposition.planes),
+            "config": {"workload": workload["label"] + ", slab-decomposed along axis 0, {} planes per GPU, {}".format(
+                           decomposition.planes,
+                           "ghost planes written by the neighbour's kernel through NVLink peer memory"
+                           if slab.exchange == "peer" else "ghost planes exchanged by NCCL send/recv (baseline mode)"),
+                       "exchange": slab.exchange,
                        "sweeps_per_exchange": 2 if slab.fused is not None else 1,
                        "ghost_planes_per_side": decomposition.g,
                        "strategy": ("temporal2 (two sweeps fused per HBM pass and per ghost exchange)" if slab.fused is not None else plan.strategy), "l2": "per-GPU slab in+out larger than L2",

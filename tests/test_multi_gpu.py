@@ -99,13 +99,17 @@ def test_slab_logic_with_gloo(world, tmp_path):
 
 
 @pytest.mark.gpu
-def test_slabs_on_two_gpus_match_single_gpu_and_oracle():
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_slabs_on_two_gpus_match_single_gpu_and_oracle(exchange):
+    """ghost planes stored by the neighbour's kernel through peer memory (the product's way), and
+    the NCCL send/recv baseline mode: both bit-identical to one GPU and to the oracle"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
     done = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "multi_gpu_check.py")],
-        capture_output=True, text=True, timeout=900, cwd=ROOT)
+         "--master-addr", "127.0.0.1", "--master-port", "29541" if exchange == "peer" else "29543",
+         os.path.join(ROOT, "tests", "multi_gpu_check.py")],
+        capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, STENCIL_CUDA_EXCHANGE=exchange))
     assert done.returncode == 0 and "MULTI_GPU_CHECK PASSED" in done.stdout, \
         done.stdout[-3000:] + done.stderr[-3000:]
