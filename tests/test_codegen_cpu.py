@@ -260,3 +260,62 @@ def test_host_pipeline_chunk_bounds():
         assert len(sizes) == 1 or min(sizes) >= min(thin, (hi - lo) // max(1, chunks))
         assert sizes[0] <= max(sizes) and sizes[-1] <= max(sizes)
     assert [b - a for a, b in zip(bounds_of(0, 512, 16, 4), bounds_of(0, 512, 16, 4)[1:])][:3] == [4, 8, 16]
+
+
+def test_padded_row_plans_address_by_pitch_and_clamp_inside_the_last_quad():
+    """iterate() on rows that are no multiple of 16 bytes: the sibling specialisation keeps the
+    true extent in the tensor map (TMA zero-fills past it), strides and store addresses use the
+    padded pitch, and under 'clamp' the column cascade starts inside the thread's quad."""
+    from cases import CONV5
+    from stencil_code_b200.backend.cuda import codegen_temporal
+    from stencil_code_b200.library.convolution import ConvolutionFilter
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+
+    class Fake(object):
+        def __init__(self, shape, dtype=numpy.float32):
+            self.shape, self.dtype, self.ndim = shape, numpy.dtype(dtype), len(shape)
+    stencil = Jacobi3D(1.0, 0.25)
+    spec = stencil.specializer
+    config = spec.args_to_subconfig((Fake((40, 66, 513)),))
+    dense = spec.transform(config)
+    assert dense.strategy == 'direct' and not dense.domain.is_pitched          # TMA stride rule
+    padded = spec.transform(config, row_pitch=516)
+    assert padded.strategy == 'stream' and padded.domain.row_pitch == 516 and padded.program.shape[-1] == 513
+    (tensor_map,) = padded.tensor_maps
+    assert tensor_map.dims == (513, 66, 40) and tensor_map.strides_bytes == (516 * 4, 66 * 516 * 4)
+    assert ") * 516 + gx" in padded.source and "if (gx + 1 > 512)" in padded.source
+    runtime.compile_source(padded.source, "padded.cu", padded.options)
+    fused = codegen_temporal.make_plan(padded.program, padded.domain, planner.B200, padded.options)
+    assert fused.tensor_maps[0].strides_bytes == (516 * 4, 66 * 516 * 4) and ") * 516 + gx" in fused.source
+    runtime.compile_source(fused.source, "padded_fused.cu", fused.options)
+    aligned = spec.transform(spec.args_to_subconfig((Fake((40, 66, 512)),)))
+    assert "if (gx + 1 > 511)" not in aligned.source                           # rows end on a quad boundary
+    with pytest.raises(ValueError):
+        spec.transform(config, row_pitch=512)                                  # pitch shorter than a row
+
+    conv = ConvolutionFilter(CONV5, boundary_handling='clamp')
+    config = conv.specializer.args_to_subconfig((Fake((700, 1025)), Fake((25,), numpy.int64)))
+    padded = conv.specializer.transform(config, row_pitch=1028)
+    assert padded.strategy == 'stream' and padded.tensor_maps[0].strides_bytes == (1028 * 4,)
+    runtime.compile_source(padded.source, "padded2d.cu", padded.options)
+
+
+def test_point_kernel_tiles_share_tap_loads():
+    """'direct' on rank-2/3 grids: RZ x RY points per thread, each distinct tap value loaded once;
+    short rows, rank 1 and STENCIL_CUDA_DIRECT=flat keep one point per thread."""
+    from stencil_code_b200.backend.cuda import codegen_direct
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    from cases import Stencil1d
+    plan = make_plan(LaplacianKernel(boundary_handling='clamp'), [((64, 96, 256), numpy.float32)], 'direct')
+    config = plan.notes['config']
+    assert config == {'kind': 'tiled', 'RY': 8, 'RZ': 2}
+    loads = [line for line in plan.source.splitlines() if line.strip().startswith("const float v0_")]
+    assert len(loads) == 68 and len(set(loads)) == 68                 # 7 taps x 16 points = 112 without sharing
+    assert plan.geometry(0, 64).grid == (2, 12, 32) and plan.geometry(10, 13).grid == (2, 12, 2)
+    runtime.compile_source(plan.source, "tiled.cu", plan.options)
+    double = make_plan(LaplacianKernel(boundary_handling='copy'), [((64, 96, 256), numpy.float64)], 'direct')
+    assert double.notes['config'] == {'kind': 'tiled', 'RY': 4, 'RZ': 2}      # doubles count twice
+    runtime.compile_source(double.source, "tiled64.cu", double.options)
+    assert make_plan(LaplacianKernel(), [((64, 96, 64), numpy.float32)], 'direct').notes['config']['kind'] == 'flat'
+    assert make_plan(Stencil1d(), [((4096,), numpy.float32)], 'direct').notes['config']['kind'] == 'flat'
+    assert codegen_direct.direct_config(plan.program, plan.domain)['kind'] == 'tiled'
