@@ -137,3 +137,14 @@ def test_iterations_keyword_and_iterate_on_the_python_backend():
     flat = numpy.random.RandomState(9).random_sample((9, 11)).astype(numpy.float32)
     conv = ConvolutionFilter(numpy.array([[0, 0.25, 0], [0.25, 0, 0.25], [0, 0.25, 0]]), backend='python')
     assert (conv(flat, iterations=2) == conv(conv(flat))).all() and (conv.iterate(flat, 2) == conv(conv(flat))).all()
+
+
+def test_jacobi_example_script_runs_on_the_python_backend():
+    """examples/jacobi_3d.py (the reference's stale example restated on the current API)"""
+    import numpy
+    from examples import jacobi_3d
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    result = jacobi_3d.main(["--backend", "python", "--shape", "5", "6", "7", "--iterations", "2"])
+    grid = numpy.random.RandomState(1).random_sample((5, 6, 7)).astype(numpy.float32)
+    stencil = Jacobi3D(alpha=0.4, beta=0.1, backend='python')
+    assert (result == stencil(stencil(grid))).all()
