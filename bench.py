@@ -6,9 +6,10 @@
 One JSON line on stdout (rank 0).  A "step" is one sweep of the workload's stencil over its grid.
 
 Workloads (BASELINE.json configs):
-  laplacian512  C2  LaplacianKernel 7-point, 512^3 float32, clamp, single pass  (default at N=1)
-  jacobi3d      C5  Jacobi3D 2048x1024x1024 float32, clamp, slab-decomposed over N GPUs with halo
-                    exchange (default at N>1; strong scaling: the grid is fixed, slabs shrink)
+  jacobi3d      C5  Jacobi3D 2048x1024x1024 float32, clamp, iterated; slab-decomposed over N GPUs
+                    with halo exchange.  THE DEFAULT AT EVERY N (strong scaling: the grid is
+                    fixed, slabs shrink; N = 1 runs the same code path on the whole grid)
+  laplacian512  C2  LaplacianKernel 7-point, 512^3 float32, clamp, single pass
   simple1024    C1  SimpleKernel 3x3 Moore, 1024^2
   conv5         C4  ConvolutionFilter 5x5, 16384^2, --boundary zero|clamp|copy|wrap|periodic
   bilateral     C3  BetterBilateralFilter radius 9, 8192^2
@@ -150,18 +151,43 @@ class ClockSampler(object):
 
 
 # ---- CPU legs --------------------------------------------------------------------------------------------
+def host_threads():
+    """Threads the CPU legs use: every core this process may run on."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def force_openmp_threads(count):
+    """`torch.distributed.run` exports OMP_NUM_THREADS=1 to its workers: override it, in the
+    environment (read when libgomp initialises) AND through the runtime call (if it already has).
+    Returns omp_get_max_threads() as the OpenMP runtime the oracle links reports it."""
+    os.environ["OMP_NUM_THREADS"] = str(count)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_dynamic(0)
+        gomp.omp_set_num_threads(int(count))
+        gomp.omp_get_max_threads.restype = ctypes.c_int
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return None
+
+
 def cpu_reference_run(workload, steps, warmup, min_seconds=0.0):
     """The restated reference OpenMP backend on this host's cores (oracle/, kind 'port').
     Runs `steps` sweeps, and keeps sweeping until `min_seconds` of CPU work have been timed."""
+    cores = host_threads()
+    force_openmp_threads(cores)
     from oracle.cref import ReferenceC, reference_args
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     stencil = workload["stencil"]
     shape = workload["cpu_shape"]
     grid = host_grid(shape, workload["scale"])
     args = reference_args(stencil, (grid,))
     variant = workload["cpu_variant"]
     compiled = ReferenceC(stencil, args, variant)
+    effective = force_openmp_threads(cores)          # the oracle's libgomp is loaded by now
     for _ in range(max(1, warmup)):
         compiled(*args)
     times = []
@@ -170,11 +196,12 @@ def cpu_reference_run(workload, steps, warmup, min_seconds=0.0):
         times.append(compiled.last_seconds)
     seconds = sum(times) / len(times)
     points = float(numpy.prod(shape))
-    return {"value": points / seconds / 1e9, "unit": "GStencil/s", "cores": cores, "kind": "port",
-            "variant": variant,
+    return {"value": points / seconds / 1e9, "unit": "GStencil/s", "cores": effective or cores, "kind": "port",
+            "variant": variant, "omp_get_max_threads": effective,
             "sample": "{} sweeps of {} = {:.1f} s of CPU work ({} backend restated from the reference, "
-                      "gcc -O2 -std=c99 -fopenmp, OMP_NUM_THREADS={})".format(
-                          len(times), "x".join(map(str, shape)), sum(times), variant, cores),
+                      "gcc -O2 -std=c99 -fopenmp, omp_get_max_threads()={} on {} usable cores; the GPU arm's grid "
+                      "is {})".format(len(times), "x".join(map(str, shape)), sum(times), variant, effective, cores,
+                                      "x".join(map(str, workload["shape"]))),
             "ms_per_sweep": seconds * 1e3}
 
 
@@ -245,20 +272,22 @@ def device_sweeps(workload, steps, warmup, iterated=False):
 def other_workloads(peak):
     """Kernel-only numbers of the remaining BASELINE configs (device-resident, synthetic data)."""
     rows = {}
-    todo = [("C1 simple1024 clamp", "simple1024", None, 200, False),
+    todo = [("C2 laplacian 512^3 clamp, single pass", "laplacian512", None, 100, False),
+            ("C1 simple1024 clamp", "simple1024", None, 200, False),
             ("C3 bilateral r9 8192^2 clamp", "bilateral", None, 3, False),
             ("C4 conv5 16384^2 zero", "conv5", "zero", 10, False),
             ("C4 conv5 16384^2 clamp", "conv5", "clamp", 10, False),
             ("C4 conv5 16384^2 wrap (== zero, as in the reference)", "conv5", "wrap", 10, False),
             ("C4 conv5 16384^2 copy", "conv5", "copy", 10, False),
             ("C4 conv5 16384^2 periodic (true wrap-around: an opt-in addition, point kernel)", "conv5", "periodic", 4, False),
-            ("C5 jacobi3d 2048x1024x1024 clamp, single sweeps", "jacobi3d", None, 6, False),
-            ("C5 jacobi3d 2048x1024x1024 clamp, iterated (two sweeps fused per HBM pass)", "jacobi3d", None, 10, True)]
+            ("C5 jacobi3d 2048x1024x1024 clamp, single sweeps (no temporal fusion)", "jacobi3d", None, 6, False)]
     for label, name, boundary, steps, iterated in todo:
         try:
             result = device_sweeps(make_workload(name, boundary, "cuda"), steps, 3, iterated)
             rows[label] = {"gstencil_s": round(result["gstencil_s"], 1), "ms_per_sweep": round(result["ms_per_sweep"], 4),
                            "frac_of_hbm_peak": round(result["gb_s"] / peak, 3), "strategy": result["strategy"]}
+            if name == "laplacian512":
+                rows[label]["e2e"] = laplacian_e2e()
             if name == "bilateral":
                 # not HBM bound: 361 taps/point at 7 instructions per tap (FSUB, FADD.RZ, LEA, LDS,
                 # FMUL, FMUL, FADD) against the FP32 issue rate of 148 SMs x 128 lanes x 1.965 GHz
@@ -270,6 +299,25 @@ def other_workloads(peak):
         except Exception as error:       # a failing extra must not lose the headline line
             rows[label] = {"error": str(error)[:200]}
     return rows
+
+
+def laplacian_e2e():
+    """C2 through the public API: stencil(pinned numpy array) -> numpy array, copies inside."""
+    from stencil_code_b200.backend.cuda import runtime
+    workload = make_workload("laplacian512", None, "cuda")
+    device = runtime.Device.get(int(os.environ.get("LOCAL_RANK", "0")))
+    host_in = device.pinned_empty(workload["shape"], numpy.float32)
+    host_in[...] = host_grid(workload["shape"], workload["scale"])
+    stencil = workload["stencil"]
+    for _ in range(2):
+        stencil(host_in)
+    begin = time.perf_counter()
+    for _ in range(5):
+        stencil(host_in)
+    seconds = (time.perf_counter() - begin) / 5
+    return {"value": float(numpy.prod(workload["shape"])) / seconds / 1e9, "unit": "GStencil/s",
+            "ms_per_step": seconds * 1e3, "h2d_bytes_per_step": int(host_in.nbytes),
+            "d2h_bytes_per_step": int(host_in.nbytes)}
 
 
 def measured_traffic(key):
@@ -341,15 +389,6 @@ def run_single_gpu(args, workload):
     checksum = float(result.ravel()[:: max(1, result.size // 4096)].sum())
 
     iterated = None
-    if args.workload == "jacobi3d":
-        # the workload is an iterated sweep (BASELINE: 100 iterations): the headline value is the
-        # iterated throughput, where pairs of sweeps are fused into one pass over HBM
-        for buffer in buffers + [out_buffer]:
-            buffer.release()
-        iterated = device_sweeps(workload, max(args.steps, 4), args.warmup, iterated=True)
-        single_value = value
-        ms_per_step = iterated["ms_per_sweep"]
-        value = iterated["gstencil_s"]
     peak, peak_source = hbm_peak()
     achieved = 8.0 * points / (ms_per_step * 1e-3) / 1e9
     info = concrete.module.function_info(plan.function)
@@ -358,14 +397,16 @@ def run_single_gpu(args, workload):
         "metric": "GStencil/s", "value": value, "unit": "GStencil/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (numpy RandomState(1) uniform)",
-        "config": {"workload": workload["label"], "strategy": plan.strategy,
+        "config": {"workload": workload["label"], "strategy": plan.strategy, "step": "one sweep of the grid",
                    "l2": "grid in+out = {:.0f} MiB, larger than the 126 MiB L2 (no flush needed)".format(
                        2 * host_in.nbytes / 2 ** 20) if 2 * host_in.nbytes > 2 * 126 * 2 ** 20 else
                    "grid fits in L2: L2-resident, launch-latency bound",
                    "kernel": dict(plan.notes.get("config", {}), grid=list(geometry.grid), block=list(geometry.block),
                                   regs=info["regs"], spill_bytes=info["local_bytes"])},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic(args.workload + ("_iterated" if iterated else "")),
+                     "traffic": measured_traffic(args.workload),
+                     "dram_frac": (measured_traffic(args.workload) / (ms_per_step * 1e-3) / 1e9 / peak)
+                     if measured_traffic(args.workload) else None,
                      "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + "
                                        "dram__bytes_write.sum per launch)",
                      "peak_source": peak_source, "algorithmic_bytes_per_launch": 8.0 * points * (2 if iterated and iterated["strategy"] == "temporal2" else 1),
@@ -392,7 +433,7 @@ def main():
     parser.add_argument("--gpus", type=int, default=1)
     parser.add_argument("--steps", type=int, default=None)
     parser.add_argument("--warmup", type=int, default=5)
-    parser.add_argument("--workload", default=None)
+    parser.add_argument("--workload", default="jacobi3d")
     parser.add_argument("--boundary", default=None)
     parser.add_argument("--impl", default="cuda", choices=("cuda", "reference"))
     parser.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -400,54 +441,51 @@ def main():
     args = parser.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    if args.workload is None:
-        args.workload = "laplacian512" if args.gpus == 1 else "jacobi3d"
     if args.steps is None:
-        # long enough for nvidia-smi to sample clocks inside the timed region (sub-millisecond sweeps)
+        # BASELINE: 100 iterations of the Jacobi sweep; the others long enough for nvidia-smi to
+        # sample clocks inside the timed region (sub-millisecond sweeps)
         args.steps = {"laplacian512": 400, "simple1024": 2000, "conv5": 200, "bilateral": 10,
-                      "jacobi3d": 40}.get(args.workload, 20)
+                      "jacobi3d": 100}.get(args.workload, 20)
 
     if args.impl == "reference":
         if rank != 0:
             return
+        force_openmp_threads(host_threads())             # before anything loads an OpenMP runtime
         workload = make_workload(args.workload, args.boundary, "python")
         base = cpu_reference_run(workload, steps=args.steps, warmup=args.warmup)
         line = {"impl": "reference", "metric": "GStencil/s", "value": base["value"], "unit": "GStencil/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": base["ms_per_sweep"], "higher_is_better": True,
-                "scaling": "weak" if args.gpus == 1 else "strong",      # as the cuda arm labels the same N
+                "scaling": "strong" if args.workload == "jacobi3d" else "weak",   # as the cuda arm labels it
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic (numpy RandomState(1) uniform)",
-                "config": {"workload": workload["label"], "cpu_grid": list(workload["cpu_shape"])},
+                "config": {"workload": workload["label"], "cpu_grid": list(workload["cpu_shape"]),
+                           "step": "one sweep of the CPU sample grid; GStencil/s is per point, so it compares "
+                                   "with the GPU arm's full grid"},
                 "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "GStencil/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
-    if args.gpus > 1 or world > 1:
+    workload = make_workload(args.workload, args.boundary, "cuda")
+    if args.workload == "jacobi3d":
         from stencil_code_b200.backend.cuda import multi_gpu_bench
-        workload = make_workload(args.workload, args.boundary, "cuda")
-        one_gpu = None
-        if rank == 0 and not args.quick:
-            # the same workload on rank 0's GPU alone, whole grid, same kernels: the denominator of
-            # a parallel efficiency (the default N=1 line is another workload, C2)
-            try:
-                alone = device_sweeps(workload, 10, 3, iterated=True)
-                from stencil_code_b200.backend.cuda import runtime
-                runtime.Device.get(int(os.environ.get("LOCAL_RANK", "0"))).trim()     # hand the 16 GiB back
-                one_gpu = {"value": alone["gstencil_s"], "unit": "GStencil/s", "ms_per_step": alone["ms_per_sweep"],
-                           "strategy": alone["strategy"],
-                           "what": "this workload, undecomposed, on one GPU of this box, iterated, 10 sweeps "
-                                   "after 4 of warm-up, timed with CUDA events before the decomposed run"}
-            except Exception as error:       # must not lose the multi-GPU line
-                one_gpu = {"error": str(error)[:200]}
         line = multi_gpu_bench.run(args, workload)
-        if line is not None:
-            if one_gpu is not None:
-                line["one_gpu_same_workload"] = one_gpu
-            print(json.dumps(line))
+        if line is None:
+            return
+        if line["n_gpus"] == 1:
+            peak, _ = hbm_peak()
+            if not args.quick:
+                line["workloads"] = other_workloads(peak)
+            if not args.no_cpu:
+                line["cpu_baseline"] = cpu_reference_run(make_workload(args.workload, args.boundary, "python"),
+                                                         steps=3, warmup=1, min_seconds=10.0)
+        print(json.dumps(line))
         return
-    print(json.dumps(run_single_gpu(args, make_workload(args.workload, args.boundary, "cuda"))))
+    if args.gpus > 1 or world > 1:
+        raise SystemExit("only the iterated workload (jacobi3d) is decomposed over several GPUs; single-pass "
+                         "configs have no exchange step (replicas only)")
+    print(json.dumps(run_single_gpu(args, workload)))
 
 
 if __name__ == "__main__":

@@ -3,6 +3,12 @@
 User code written against ucb-sejits/stencil_code imports ``stencil_code.stencil_kernel``,
 ``stencil_code.neighborhood``, ``stencil_code.library.<kernel>`` ...; this package maps those
 module paths onto the B200 implementation so such code runs unmodified (on ``backend='cuda'``).
+
+Importing this package also makes the reference's backend names -- ``backend='c'``, ``'omp'``,
+``'ocl'``, ``'opencl'``, which reference user code passes explicitly and
+``BetterBilateralFilter`` defaults to -- select ``'cuda'`` (with a one-time warning) instead of
+raising; results follow the reference's C backend.
+``STENCIL_CUDA_LEGACY_BACKENDS=raise`` restores the strict behaviour.
 """
 import importlib
 import sys
@@ -19,6 +25,8 @@ _MODULES = [
 ]
 for _name in _MODULES:
     sys.modules[__name__ + "." + _name] = importlib.import_module("stencil_code_b200." + _name)
+
+_impl.stencil_kernel.LEGACY_BACKENDS_RUN_ON_CUDA[0] = True
 
 Stencil = _impl.Stencil
 Neighborhood = _impl.Neighborhood

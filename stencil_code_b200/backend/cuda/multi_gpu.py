@@ -154,6 +154,7 @@ class SlabStencil(object):
         self.edge_done = self.device.new_event()
         self.interior_done = self.device.new_event()
         self._events_armed = False
+        self._ghosts_stale = False
         self.peers = {}
         self.exchange = os.environ.get("STENCIL_CUDA_EXCHANGE", "peer") if slab.ghosted else "none"
         if self.exchange not in ("peer", "nccl", "none"):
@@ -233,7 +234,28 @@ class SlabStencil(object):
             for work in dist.batch_isend_irecv(operations):
                 work.wait()                      # stream-ordered: the edge stream waits, not the host
 
+    def quiesce(self):
+        """All ranks have finished every enqueued sweep: no neighbour kernel can still be storing
+        into this rank's ghost planes (they are written through peer mappings, outside this
+        rank's streams)."""
+        self.synchronize()
+        if self.slab.ghosted:
+            self.dist.barrier()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
     def close(self):
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        try:
+            self.quiesce()
+        except Exception:
+            pass
         if self.exchange != "peer":
             self.peers = {}
             return
@@ -250,6 +272,8 @@ class SlabStencil(object):
         """Counter-based uniform [0, scale) fill, a function of the GLOBAL element index, so every
         decomposition of the same grid holds the same values (ghost planes included)."""
         slab = self.slab
+        self.quiesce()
+        self._ghosts_stale = False
         first_global = slab.start - slab.first_real            # global plane of local plane 0
         count = int(numpy.prod(slab.local_shape, dtype=numpy.int64))
         offset = first_global * slab.plane_elems               # may be negative on rank 0: wraps, unused
@@ -261,9 +285,68 @@ class SlabStencil(object):
         if slab.ghosted:
             self.dist.barrier()
 
+    def host_window(self):
+        """Global axis-0 plane range [lo, hi) this rank needs from the host: its real planes plus
+        the ghost planes that border another slab."""
+        slab = self.slab
+        lo = max(0, slab.start - slab.first_real)
+        hi = min(slab.global_shape[0], slab.stop + (slab.g if slab.ghosted else 0))
+        return lo, hi
+
+    def apply_host(self, window, out=None):
+        """ONE sweep, host memory to host memory, on this rank's slab: ``window`` holds the global
+        planes ``host_window()`` (C-contiguous float32, ideally pinned); returns this rank's real
+        planes of the result as a (pinned) host array.  The ghost planes come from the host
+        window, so no exchange between the GPUs is needed; copy-in, sweep and copy-out are
+        pipelined in axis-0 chunks on three streams (``ConcreteCudaStencil.sweep_host``).
+        The device buffers keep the sweep's result: ``iterate()`` may follow."""
+        slab = self.slab
+        self.quiesce()
+        lo, hi = self.host_window()
+        window = numpy.ascontiguousarray(window, dtype=numpy.float32)
+        if window.shape != (hi - lo,) + slab.global_shape[1:]:
+            raise StencilException("apply_host needs planes {}..{} of the global grid".format(lo, hi))
+        shape = (slab.planes,) + slab.global_shape[1:]
+        if out is None:
+            out = self.device.pinned_empty(shape, numpy.float32)
+        elif out.shape != shape or out.dtype != numpy.float32 or not out.flags.c_contiguous:
+            raise StencilException("out= must be a C-contiguous float32 array of this rank's real planes")
+        local_lo = lo - (slab.start - slab.first_real)
+        current = self.buffers[self.step % 2].ptr
+        target = self.buffers[(self.step + 1) % 2].ptr
+        first = slab.first_real
+        plane_bytes = slab.plane_elems * 4
+        self.concrete.sweep_host(window.ctypes.data, (local_lo, local_lo + (hi - lo)),
+                                 [current] + [b.ptr for b in self.table_buffers], target,
+                                 out.ctypes.data - first * plane_bytes, (first, first + slab.planes))
+        self.step += 1
+        self.sweep += 1
+        if slab.ghosted:
+            # the target buffer's ghost planes were not refreshed: iterate() must not trust them
+            self._ghosts_stale = True
+        return out
+
+    def _refresh_ghosts(self):
+        """Bring the ghost planes of the current buffer up to date from the neighbours' real
+        planes (after ``apply_host``, which computes real planes only)."""
+        slab = self.slab
+        index = self.step % 2
+        self.quiesce()
+        if self.exchange == "nccl":
+            self._exchange_nccl(index)
+        else:
+            plane_bytes = slab.plane_elems * 4
+            for neighbour, source, destination in slab.sends():
+                self.runtime.check(self.library.sc_memcpy_d2d_async(
+                    ctypes.c_void_p(self.peers[neighbour]["buffers"][index] + destination[0] * plane_bytes),
+                    ctypes.c_void_p(self.buffers[index].ptr + source[0] * plane_bytes),
+                    (source[1] - source[0]) * plane_bytes, self.edge_stream))
+        self.quiesce()
+        self._ghosts_stale = False
+
     def load(self, global_grid):
         """Copy this rank's planes (plus ghost planes) of a host array of the global shape."""
-        self.synchronize()
+        self.quiesce()
         slab = self.slab
         lo = max(0, slab.start - slab.first_real)
         hi = min(slab.global_shape[0], slab.stop + (slab.g if slab.ghosted else 0))
@@ -275,13 +358,25 @@ class SlabStencil(object):
         self.device.synchronize()
         if slab.ghosted:
             self.dist.barrier()
+        self._ghosts_stale = False
 
-    def result(self):
+    def launches_per_step(self):
+        """kernel launches one ``iterate`` step enqueues on this rank (a step = one sweep, or a
+        fused pair of sweeps)"""
+        if not self.slab.ghosted:
+            return 1
+        edges = int(self.slab.open_lo) + int(self.slab.open_hi)
+        return 1 + edges + (1 if self.exchange == "peer" else 0)
+
+    def result(self, out=None):
         """This rank's real planes as a host array."""
         self.synchronize()
         slab = self.slab
         shape = (slab.planes,) + slab.global_shape[1:]
-        out = self.device.pinned_empty(shape, numpy.float32)
+        if out is None:
+            out = self.device.pinned_empty(shape, numpy.float32)
+        elif out.shape != shape or out.dtype != numpy.float32 or not out.flags.c_contiguous:
+            raise StencilException("out= must be a C-contiguous float32 array of this rank's real planes")
         source = self._current().ptr + slab.first_real * slab.plane_elems * 4
         self.runtime.check(self.library.sc_memcpy_d2h_async(
             ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(source), out.nbytes, self.device.stream))
@@ -334,6 +429,17 @@ class SlabStencil(object):
         runtime, library = self.runtime, self.library
         main, edge = self.device.stream, self.edge_stream
         tables = [b.ptr for b in self.table_buffers]
+        if self._ghosts_stale and sweeps > 0:
+            self._refresh_ghosts()
+        if not slab.ghosted:
+            # one GPU: the same enqueue-from-C ping-pong (programmatic dependent launch, fused
+            # pairs of sweeps) that ``stencil.iterate`` uses
+            current, spare = self.buffers[self.step % 2].ptr, self.buffers[(self.step + 1) % 2].ptr
+            final = self.concrete.sweeps(current, spare, tables, sweeps, main, allow_fused=self.fused is not None)
+            if final != current:
+                self.step += 1
+            self.sweep += sweeps
+            return
         top, interior, bottom = slab.ranges()
         up, down = self.peers.get(slab.rank - 1), self.peers.get(slab.rank + 1)
         plane = slab.plane_elems

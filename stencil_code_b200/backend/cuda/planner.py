@@ -1,7 +1,8 @@
 """Tiling / launch-geometry planner of the CUDA backend.
 
 Replaces reference ``backend/local_size_computer.py:17-253`` (the OpenCL work-group shape
-chooser) and the global-size logic of ``backend/ocl_boundary_copier.py:69-84``.  Like the
+chooser); the per-dimension halo kernels of ``backend/ocl_boundary_copier.py:69-84`` have no
+counterpart: every generated kernel handles its own boundary points.  Like the
 reference's planner it is pure host arithmetic over a device-properties record, so it can be
 unit-tested with a fake device (the reference does that with ``MockDevice``,
 ``test/fixtures.py:3-11``); unlike it, it chooses between code-generation strategies:
@@ -64,11 +65,3 @@ def plan(program, domain, device_props=None, forced_strategy=None, options=()):
 
     return CudaPlan(program, domain, 'direct', source, 'stencil_direct', options, geometry,
                     notes={'why': reason, 'config': config})
-
-
-def halo_slabs(shape, ghost_depth):
-    """The disjoint slab cover of the halo shell used by ``HaloEnumerator`` as index ranges --
-    the device-side decomposition that replaces one OpenCL boundary kernel per dimension
-    (reference ``backend/ocl_boundary_copier.py:69-84``)."""
-    from ...halo_enumerator import HaloEnumerator
-    return [tuple((r.start, r.stop) for r in slab) for slab in HaloEnumerator(ghost_depth, shape).slabs()]

@@ -331,9 +331,26 @@ class Device(object):
             pointer = raw.value
         block = (ctypes.c_char * nbytes).from_address(pointer)
         array = numpy.frombuffer(block, dtype=dtype, count=count).reshape(shape)
-        weakref.finalize(block, self._free_pinned.setdefault(nbytes, []).append, pointer)
-        _PINNED_RANGES.append((pointer, pointer + nbytes))
+        weakref.finalize(block, self._recycle_pinned, pointer, nbytes)
         return array
+
+    PINNED_POOL_LIMIT = 4 << 30         # bytes of idle page-locked blocks kept for reuse
+
+    def _recycle_pinned(self, pointer, nbytes):
+        """An array from pinned_empty died: keep its block for the next call of the same size.
+        The idle pool is bounded: beyond PINNED_POOL_LIMIT older idle blocks go back to the
+        driver, so that at most the limit -- or one single larger block -- stays page-locked."""
+        library = load_library()
+        pool = self._free_pinned
+        idle = sum(size * len(bucket) for size, bucket in pool.items())
+        for size in list(pool):
+            bucket = pool[size]
+            while bucket and idle + nbytes > self.PINNED_POOL_LIMIT:
+                library.sc_host_free(ctypes.c_void_p(bucket.pop(0)))
+                idle -= size
+            if not bucket:
+                del pool[size]
+        pool.setdefault(nbytes, []).append(pointer)
 
     # -- helper kernels (csrc/device_utils.cu)
     def utils(self):
@@ -349,19 +366,11 @@ class Device(object):
         return self._utils
 
 
-_PINNED_RANGES = []
-
-
 def pinned_empty(shape, dtype=numpy.float32, device_index=None):
     """Uninitialised numpy array in page-locked host memory (fast, asynchronous transfers)."""
     if isinstance(shape, int):
         shape = (shape,)
     return Device.get(device_index).pinned_empty(tuple(shape), dtype)
-
-
-def is_pinned(array):
-    address = array.ctypes.data
-    return any(lo <= address < hi for lo, hi in _PINNED_RANGES)
 
 
 class DeviceBuffer(object):
@@ -450,9 +459,11 @@ class ConcreteCudaStencil(object):
             check(load_library().sc_tensormap_tiled(ctypes.byref(tmap), ctypes.c_void_p(pointer),
                                                     spec.dtype_code, rank, dims, strides, box, 0),
                   "tensor map encode")
-            if len(self._tmaps) > 64:
-                self._tmaps.clear()
-            self._tmaps[key] = tmap
+            while len(self._tmaps) >= 256:          # least recently used goes first
+                self._tmaps.pop(next(iter(self._tmaps)))
+        else:
+            del self._tmaps[key]                    # re-insert: dicts keep insertion order
+        self._tmaps[key] = tmap
         return tmap
 
     def launch(self, arg_pointers, out_pointer, a0_begin=None, a0_end=None, stream=None,
@@ -493,9 +504,11 @@ class ConcreteCudaStencil(object):
             prepared = (values, pointers, (ctypes.c_uint32 * 3)(*geometry.grid),
                         (ctypes.c_uint32 * 3)(*geometry.block), (ctypes.c_uint32 * 3)(*geometry.cluster),
                         geometry.smem, function.encode())
-            if len(self._launches) > 256:
-                self._launches.clear()
-            self._launches[key] = prepared
+            while len(self._launches) >= 1024:
+                self._launches.pop(next(iter(self._launches)))
+        else:
+            del self._launches[key]
+        self._launches[key] = prepared
         if prepare_only:
             return prepared
         _, pointers, grid, block, cluster, smem, name = prepared
@@ -537,14 +550,32 @@ class ConcreteCudaStencil(object):
             raise StencilException("tensor is on cuda:{} but the stencil was specialised on cuda:{}"
                                    .format(grid.device.index, self.device.index))
 
+    def _check_out_tensor(self, out, tensors):
+        """A caller-supplied ``out=`` tensor is written by the kernel as it stands: it must be a
+        contiguous CUDA tensor on this device with the grid's shape and dtype, and must not share
+        memory with any input (a sweep cannot run in place)."""
+        grid = tensors[0]
+        if not _is_torch_tensor(out) or not out.is_cuda or out.device.index != self.device.index:
+            raise StencilException("out= must be a torch tensor on cuda:{}".format(self.device.index))
+        if tuple(out.shape) != tuple(grid.shape) or out.dtype != grid.dtype or not out.is_contiguous():
+            raise StencilException("out= must be a contiguous tensor of the grid's shape and dtype")
+        first = out.data_ptr()
+        last = first + out.numel() * out.element_size()
+        for tensor in tensors:
+            begin = tensor.data_ptr()
+            if begin < last and first < begin + tensor.numel() * tensor.element_size():
+                raise StencilException("out= must not overlap an input (a sweep cannot run in place)")
+
     def _call_torch(self, args, out):
         import torch
         grid = args[0]
         self._require_device_tensor(grid)
         tensors = _device_tensors(args)
-        result = torch.empty_like(tensors[0]) if out is None else out
-        if not result.is_contiguous():
-            raise StencilException("out= must be contiguous")
+        if out is None:
+            result = torch.empty_like(tensors[0])
+        else:
+            self._check_out_tensor(out, tensors)
+            result = out
         stream = ctypes.c_void_p(torch.cuda.current_stream(grid.device).cuda_stream)
         self.launch([t.data_ptr() for t in tensors], result.data_ptr(), stream=stream)
         return result
@@ -590,67 +621,92 @@ class ConcreteCudaStencil(object):
             result = out
         buffers = [device.alloc(a.nbytes) for a in arrays]
         out_buffer = device.alloc(grid.nbytes)
-        compute, copy_in, copy_out = device.stream, device.h2d_stream, device.d2h_stream
         lo, hi = self.plan.domain.sweep_range
+        for array, buffer in zip(arrays[1:], buffers[1:]):
+            check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(array.ctypes.data),
+                                              array.nbytes, device.stream))
         plane_bytes = grid.nbytes // max(1, grid.shape[0])
-        ghost = self.program.ghost_depth[0]
-        chunks = 1
-        if grid.nbytes >= self.PIPELINE_MIN_BYTES and grid.ndim >= 2 and self.program.boundary != 'periodic':
-            # (periodic: the first chunk reads the last planes -- everything must have landed)
-            chunks = max(1, min(64, grid.nbytes // self.PIPELINE_CHUNK_BYTES, (hi - lo) // max(1, 4 * ghost)))
-        if chunks <= 1:
-            for array, buffer in zip(arrays, buffers):
-                check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(array.ctypes.data),
-                                                  array.nbytes, compute))
-            self.launch([b.ptr for b in buffers], out_buffer.ptr, stream=compute)
-            check(library.sc_memcpy_d2h_async(ctypes.c_void_p(result.ctypes.data), ctypes.c_void_p(out_buffer.ptr),
-                                              result.nbytes, compute))
-            device.synchronize(compute)
-        else:
-            bounds = self._pipeline_bounds(lo, hi, chunks, 4 * ghost)
-            chunks = len(bounds) - 1
-            # head[k]: the first `ghost` planes of chunk k are on the device -- all that the sweep
-            # of chunk k-1 needs from it; landed: everything is
-            head = [device.event() for _ in range(chunks)]
-            landed = [device.event()]
-            swept = [device.event() for _ in range(chunks)]
-            # make sure earlier work on the compute stream (a previous call) is not overtaken
-            fence = device.event()
-            check(library.sc_event_record(fence, compute))
-            check(library.sc_stream_wait_event(copy_in, fence))
-            for array, buffer in zip(arrays[1:], buffers[1:]):
-                check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffer.ptr), ctypes.c_void_p(array.ctypes.data),
-                                                  array.nbytes, copy_in))
-            for k in range(chunks):
-                split = min(bounds[k] + max(ghost, 1), bounds[k + 1])
-                for begin, end, event in ((bounds[k], split, head[k]), (split, bounds[k + 1], None)):
-                    if end > begin:
-                        check(library.sc_memcpy_h2d_async(ctypes.c_void_p(buffers[0].ptr + begin * plane_bytes),
-                                                          ctypes.c_void_p(grid.ctypes.data + begin * plane_bytes),
-                                                          (end - begin) * plane_bytes, copy_in))
-                    if event is not None:
-                        check(library.sc_event_record(event, copy_in))
-            check(library.sc_event_record(landed[0], copy_in))
-            pointers = [b.ptr for b in buffers]
-            for k in range(chunks):
-                # chunk k reads the first ghost planes of chunk k+1; the copies are in stream order,
-                # so those having landed implies that chunk k has
-                check(library.sc_stream_wait_event(compute, head[k + 1] if k + 1 < chunks else landed[0]))
-                self.launch(pointers, out_buffer.ptr, bounds[k], bounds[k + 1], stream=compute)
-                check(library.sc_event_record(swept[k], compute))
-                check(library.sc_stream_wait_event(copy_out, swept[k]))
-                offset = bounds[k] * plane_bytes
-                size = (bounds[k + 1] - bounds[k]) * plane_bytes
-                check(library.sc_memcpy_d2h_async(ctypes.c_void_p(result.ctypes.data + offset),
-                                                  ctypes.c_void_p(out_buffer.ptr + offset), size, copy_out))
-            landed = landed + head
-            device.synchronize(copy_out)
-            device.synchronize(compute)
-            for event in landed + swept + [fence]:
-                device.recycle_event(event)
+        self.sweep_host(grid.ctypes.data, (0, grid.shape[0]), [b.ptr for b in buffers], out_buffer.ptr,
+                        result.ctypes.data - lo * plane_bytes, (lo, hi),
+                        pipelined=grid.ndim >= 2 and self.program.boundary != 'periodic')
+        # (periodic: the first chunk reads the last planes -- everything must have landed)
         for buffer in buffers + [out_buffer]:
             buffer.release()
         return result
+
+    def sweep_host(self, host_in, in_range, pointers, out_pointer, host_out, out_range, pipelined=True):
+        """One sweep with the grid coming from and the result going to HOST memory, synchronous.
+
+        ``host_in`` is the address of axis-0 planes ``in_range`` = [first, last) of the (local)
+        grid; they are copied to the same planes of the device buffer ``pointers[0]`` (tables,
+        ``pointers[1:]``, must already be on the device, enqueued on the compute stream).  The
+        sweep writes planes ``out_range`` of the device buffer ``out_pointer``, which are copied
+        to ``host_out + plane * plane_bytes``.  Large transfers are cut into axis-0 chunks on
+        three streams: copy-in of chunk i+1, sweep of chunk i and copy-out of chunk i-1 overlap.
+        Used by ``stencil(numpy_array)`` and, per rank, by ``SlabStencil.apply_host``."""
+        library = load_library()
+        device = self.device
+        compute, copy_in, copy_out = device.stream, device.h2d_stream, device.d2h_stream
+        shape = self.program.shape
+        plane_bytes = self.program.out_dtype_size * int(numpy.prod(shape[1:], dtype=numpy.int64)) \
+            if len(shape) > 1 else self.program.out_dtype_size
+        in_lo, in_hi = in_range
+        lo, hi = out_range
+        ghost = self.program.ghost_depth[0]
+        nbytes = (hi - lo) * plane_bytes
+        chunks = 1
+        if pipelined and nbytes >= self.PIPELINE_MIN_BYTES:
+            chunks = max(1, min(64, nbytes // self.PIPELINE_CHUNK_BYTES, (hi - lo) // max(1, 4 * ghost)))
+
+        def copy_in_planes(begin, end, stream):
+            begin, end = max(begin, in_lo), min(end, in_hi)
+            if end > begin:
+                check(library.sc_memcpy_h2d_async(ctypes.c_void_p(pointers[0] + begin * plane_bytes),
+                                                  ctypes.c_void_p(host_in + (begin - in_lo) * plane_bytes),
+                                                  (end - begin) * plane_bytes, stream))
+
+        def copy_out_planes(begin, end, stream):
+            check(library.sc_memcpy_d2h_async(ctypes.c_void_p(host_out + begin * plane_bytes),
+                                              ctypes.c_void_p(out_pointer + begin * plane_bytes),
+                                              (end - begin) * plane_bytes, stream))
+        if chunks <= 1:
+            copy_in_planes(in_lo, in_hi, compute)
+            self.launch(pointers, out_pointer, lo, hi, stream=compute)
+            copy_out_planes(lo, hi, compute)
+            device.synchronize(compute)
+            return
+        bounds = self._pipeline_bounds(lo, hi, chunks, 4 * ghost)
+        chunks = len(bounds) - 1
+        # head[k]: the first `ghost` planes of chunk k are on the device -- all that the sweep
+        # of chunk k-1 needs from it; landed: everything is
+        head = [device.event() for _ in range(chunks)]
+        landed = device.event()
+        swept = [device.event() for _ in range(chunks)]
+        # make sure earlier work on the compute stream (a previous call, the tables) is not overtaken
+        fence = device.event()
+        check(library.sc_event_record(fence, compute))
+        check(library.sc_stream_wait_event(copy_in, fence))
+        check(library.sc_stream_wait_event(copy_out, fence))
+        for k in range(chunks):
+            first = in_lo if k == 0 else bounds[k]                  # planes below the sweep range ride along
+            last = in_hi if k == chunks - 1 else bounds[k + 1]
+            split = min(bounds[k] + max(ghost, 1), last)
+            copy_in_planes(first, split, copy_in)
+            check(library.sc_event_record(head[k], copy_in))
+            copy_in_planes(split, last, copy_in)
+        check(library.sc_event_record(landed, copy_in))
+        for k in range(chunks):
+            # chunk k reads the first ghost planes of chunk k+1; the copies are in stream order,
+            # so those having landed implies that chunk k has
+            check(library.sc_stream_wait_event(compute, head[k + 1] if k + 1 < chunks else landed))
+            self.launch(pointers, out_pointer, bounds[k], bounds[k + 1], stream=compute)
+            check(library.sc_event_record(swept[k], compute))
+            check(library.sc_stream_wait_event(copy_out, swept[k]))
+            copy_out_planes(bounds[k], bounds[k + 1], copy_out)
+        device.synchronize(copy_out)
+        device.synchronize(compute)
+        for event in head + swept + [fence, landed]:
+            device.recycle_event(event)
 
     # -- temporal blocking ----------------------------------------------------------------------
     def temporal(self):
@@ -778,12 +834,12 @@ class ConcreteCudaStencil(object):
             modules[id(plan)] = module
         return module
 
-    def sweeps(self, pointers_a, pointer_b, table_pointers, count, stream):
+    def sweeps(self, pointers_a, pointer_b, table_pointers, count, stream, allow_fused=True):
         """``count`` sweeps ping-ponging between device buffers a and b (a holds the input).
         Pairs of sweeps run as one fused launch where temporal blocking applies.  Returns the
         pointer that holds the result."""
         current, spare = pointers_a, pointer_b
-        fused = self.temporal()
+        fused = self.temporal() if allow_fused else None
         stream = self.device.stream if stream is None else stream
         remaining = count
 

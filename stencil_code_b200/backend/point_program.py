@@ -187,6 +187,10 @@ class PointProgram(object):
         self.boundary = boundary          # 'clamp' | 'zero' | 'copy' | 'periodic'   ('wrap' arrives as 'zero')
 
     @property
+    def out_dtype_size(self):
+        return 8 if self.out_ctype == DOUBLE else 4
+
+    @property
     def npoints(self):
         n = 1
         for s in self.shape:
@@ -267,8 +271,11 @@ def _exact_in_float(expr):
 
     * a float-typed sub-expression promoted to double: itself
     * a double literal that is exactly a float32: the float literal
-    * (+-2^k) * x with x as above: the product is exact in binary floating point (barring
-      underflow into the float32 subnormal range, documented in DESIGN.md)
+    * (+-2^k) * x with x as above: the product is exact in binary floating point as long as it
+      neither overflows float32 nor falls into its subnormal range.  Precondition (DESIGN.md
+      section 4): |x| * 2^k within [2^-126, 2^128) -- any data of physical magnitude; inputs near
+      FLT_MAX or FLT_MIN need STENCIL_CUDA_STRICT=1, which keeps the double arithmetic
+      (tests/test_gpu_parity.py::test_extreme_magnitudes_need_strict_mode).  1.0 * x is x.
     """
     if expr.ctype in (INT, LONG):
         return None
@@ -284,6 +291,8 @@ def _exact_in_float(expr):
                     and _is_float_exact_const(const.value):
                 inner = _exact_in_float(other)
                 if inner is not None:
+                    if const.value == 1.0:
+                        return inner                  # 1.0 * x is x, bit for bit (-0.0, inf, NaN included)
                     if const is expr.left:
                         return Bin('*', Const(const.value, FLOAT), inner, FLOAT)
                     return Bin('*', inner, Const(const.value, FLOAT), FLOAT)
@@ -297,6 +306,10 @@ def _single_op_in_float(expr):
     if isinstance(expr, Bin) and expr.ctype == DOUBLE and expr.op in '+-*/':
         left, right = _exact_in_float(expr.left), _exact_in_float(expr.right)
         if left is not None and right is not None:
+            if expr.op == '*':                        # 1.0 * x is x, bit for bit
+                for const, other in ((left, right), (right, left)):
+                    if isinstance(const, Const) and const.value == 1.0:
+                        return other
             return Bin(expr.op, left, right, FLOAT)
     return _exact_in_float(expr)
 

@@ -3,10 +3,9 @@
 Behavioural mirror of reference ``stencil_code/halo_enumerator.py:5-86``.  The shell is covered
 dimension by dimension: for dimension k the low slab ``[0, h_k)`` and the high slab
 ``[n_k - h_k, n_k)`` are emitted with every dimension < k already restricted to its interior
-(so no point is produced twice) and every dimension > k spanning its full extent.  The same
-slab decomposition drives the CUDA backend's boundary planning
-(``backend/cuda/planner.py:halo_slabs``), replacing reference
-``backend/ocl_boundary_copier.py:69-84``.
+(so no point is produced twice) and every dimension > k spanning its full extent.  It serves
+``Stencil.halo_points`` (the python backend's 'copy' mode); the CUDA kernels handle their halo
+points themselves and do not use it.
 """
 import itertools
 

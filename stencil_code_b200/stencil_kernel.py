@@ -45,6 +45,18 @@ def _backend_table():
     return {"cuda": StencilCudaTransformer}
 
 
+_LEGACY_WARNED = set()
+LEGACY_BACKENDS_RUN_ON_CUDA = [False]        # switched on by importing the ``stencil_code`` alias package
+
+
+def legacy_backends_run_on_cuda():
+    import os
+    setting = os.environ.get("STENCIL_CUDA_LEGACY_BACKENDS", "")
+    if setting:
+        return setting == "cuda"
+    return LEGACY_BACKENDS_RUN_ON_CUDA[0]
+
+
 class SpecializedStencil(object):
     """JIT driver for one ``Stencil`` instance and one backend."""
 
@@ -104,6 +116,7 @@ class SpecializedStencil(object):
             concrete = self.finalize(self.transform(arg_cfg, open_faces, slab_ghost, row_pitch))
             concrete.origin = (self, arg_cfg)        # lets a callable ask for a sibling specialisation
             self._cache[key] = concrete
+        self.args = None                             # do not keep the caller's arrays alive
         return concrete
 
     def __call__(self, *args, **kwargs):
@@ -151,9 +164,22 @@ class Stencil(object):
         if backend not in self.backend_dict:
             raise StencilException("Error: unknown backend '{}'".format(backend))
         if backend not in ('cuda', 'python'):
-            raise StencilException(
-                "Error: backend '{}' is not part of this build; use backend='cuda' (or 'python' "
-                "for the literal interpreter)".format(backend))
+            # 'c', 'omp', 'ocl', 'opencl': the reference's specialising backends.  User code
+            # written for the reference names them explicitly (its tests and benchmarks pass
+            # backend='c' / 'ocl'; ``BetterBilateralFilter`` defaults to 'ocl',
+            # ``library/better_bilateral_filter.py:18``).  Under the ``stencil_code`` alias package
+            # (or STENCIL_CUDA_LEGACY_BACKENDS=cuda) such requests run on the one specialising
+            # backend of this build, with the C backend's boundary semantics; otherwise they raise.
+            if not legacy_backends_run_on_cuda():
+                raise StencilException(
+                    "Error: backend '{}' is not part of this build; use backend='cuda' (or 'python' "
+                    "for the literal interpreter)".format(backend))
+            if backend not in _LEGACY_WARNED:
+                _LEGACY_WARNED.add(backend)
+                import warnings
+                warnings.warn("stencil_code: backend='{}' runs on backend='cuda' in this build "
+                              "(results follow the reference's C backend)".format(backend), stacklevel=2)
+            backend = 'cuda'
         self.backend = self.backend_dict[backend]
         self.backend_name = backend
 

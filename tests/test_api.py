@@ -62,10 +62,17 @@ def test_default_distance():
     assert jacobi.distance((3, 0), (0, 4)) == 5.0
 
 
-def test_backends_that_need_ctree_raise():
+def test_backends_that_need_ctree_raise(monkeypatch):
+    """strict mode (the default of ``stencil_code_b200``; importing the ``stencil_code`` alias
+    package maps the reference's backend names to 'cuda' instead, tests/test_reference_crosscheck.py)"""
+    monkeypatch.setenv("STENCIL_CUDA_LEGACY_BACKENDS", "raise")
     for name in ('c', 'omp', 'ocl', 'opencl', 'nope'):
         with pytest.raises(StencilException):
             Jacobi(backend=name)
+    monkeypatch.setenv("STENCIL_CUDA_LEGACY_BACKENDS", "cuda")
+    with pytest.raises(StencilException):
+        Jacobi(backend='nope')
+    assert Jacobi(backend='omp').backend_name == 'cuda'
 
 
 def test_backend_base_requires_visit_interior_points_loop():

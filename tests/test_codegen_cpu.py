@@ -126,13 +126,6 @@ def test_unaligned_rows_fall_back_to_direct(monkeypatch):
         make_plan(SimpleKernel(), [((102, 7), numpy.float32)], 'stream')
 
 
-def test_halo_slabs_cover_matches_enumerator():
-    from stencil_code_b200.halo_enumerator import HaloEnumerator
-    slabs = planner.halo_slabs((6, 7, 8), (1, 2, 1))
-    count = sum((a1 - a0) * (b1 - b0) * (c1 - c0) for (a0, a1), (b0, b1), (c0, c1) in slabs)
-    assert count == len(list(HaloEnumerator((1, 2, 1), (6, 7, 8)))) == 6 * 7 * 8 - 4 * 3 * 6
-
-
 # ---- large neighborhoods: tiled plane kernels with re-rolled neighbor loops ------------------------
 def bilateral_plan(shape=(256, 512), sigma_d=3):
     from stencil_code_b200.library.better_bilateral_filter import BetterBilateralFilter

@@ -1,6 +1,7 @@
-"""Parity at BASELINE.json's full sizes, where no CPU oracle finishes in seconds.
+"""Consistency of the generated code paths at BASELINE.json's full sizes, device-resident.
 
-Device-resident throughout.  Two kinds of evidence:
+(The comparison with the CPU oracle at these sizes is ``tests/test_gpu_baseline_oracle.py``; this
+file adds what needs no host round trip.)  Two kinds of evidence:
   * the independently generated code paths -- 'direct' (one thread per point, global loads),
     'stream' (TMA pipeline) and, for iterated sweeps, the fused two-sweep kernel -- must agree
     bit for bit on the full grid (``sc_count_diff`` counts differing bit patterns on the device);

@@ -72,6 +72,7 @@ def test_reference_made_fixtures(case, mode):
 SHAPE_SWEEP = {
     "laplacian": [(5, 5, 5), (3, 4, 7), (33, 20, 132), (16, 40, 256), (70, 37, 64), (4, 130, 136)],
     "jacobi3d": [(40, 24, 128), (19, 65, 260)],
+    "jacobi2d": [(128, 128), (130, 260), (1024, 1024)],       # reference test/test_c_end_to_end.py:72-74 (128^2)
     "simple_moore": [(5, 5), (102, 7), (64, 128), (130, 260), (37, 1024), (300, 516)],
     "convolution5_modes": [(8, 8), (64, 128), (131, 388), (50, 1028)],
     "diagnostic": [(8, 8), (96, 256), (45, 132)],
@@ -353,3 +354,73 @@ def test_point_kernel_flat_and_tiled_forms_agree(mode, monkeypatch):
             assert concrete.plan.notes['config']['kind'] == form
             actual = stencil(grid, *tables)
             assert (actual.view(view) == expected.view(view)).all(), (form, shape, mode)
+
+
+def test_out_tensor_is_validated():
+    """A caller-supplied out= tensor is handed to the kernel as it stands: wrong shape, dtype,
+    device, layout or aliasing must raise instead of writing out of bounds."""
+    import torch
+    from stencil_code_b200.library.laplacian import LaplacianKernel
+    stencil = LaplacianKernel()
+    grid = torch.rand((16, 24, 128), device="cuda")
+    good = torch.empty_like(grid)
+    assert stencil(grid, out=good) is good
+    expected = oracle_output(LaplacianKernel(backend='python'), grid.cpu().numpy())
+    assert_bit_identical(good.cpu().numpy(), expected)
+    for bad in (torch.empty((16, 24, 64), device="cuda"),                       # smaller
+                torch.empty((16, 24, 128), device="cuda", dtype=torch.float64),  # wrong dtype
+                torch.empty((16, 24, 128)),                                      # host tensor
+                torch.empty((16, 24, 256), device="cuda")[:, :, ::2],            # not contiguous
+                grid,                                                            # in place
+                numpy.empty((16, 24, 128), numpy.float32)):                      # not a tensor
+        with pytest.raises(StencilException, match="out="):
+            stencil(grid, out=bad)
+    overlapping = torch.empty(2 * grid.numel(), device="cuda")
+    source = overlapping[:grid.numel()].view(grid.shape)
+    with pytest.raises(StencilException, match="overlap"):
+        stencil(source, out=overlapping[128:128 + grid.numel()].view(grid.shape))
+
+
+def test_extreme_magnitudes_need_strict_mode(monkeypatch):
+    """The exact float32 demotion of (+-2^k) * x holds while the product neither overflows nor
+    becomes subnormal.  Ordinary magnitudes: demoted == strict == oracle.
+    Near FLT_MAX / FLT_MIN only STENCIL_CUDA_STRICT=1 (double arithmetic kept) matches the
+    reference's C bit for bit -- the documented precondition, pinned here."""
+    from stencil_code_b200.library.diagnostic_stencil import DiagnosticStencil       # weights 2, 4, 8, 16
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D                         # weight 0.25
+    rng = numpy.random.RandomState(3)
+    signs = numpy.where(rng.random_sample((24, 128)) < 0.5, -1.0, 1.0)
+    huge = (signs * rng.uniform(0.3, 0.9, (24, 128)) * 3.0e38 / 16).astype(numpy.float32)   # 16 * x stays finite
+    tiny = (rng.uniform(1.0, 8.0, (8, 16, 128)) * 1.2e-38).astype(numpy.float32)             # 0.25 * x is subnormal
+    monkeypatch.setenv("STENCIL_CUDA_STRICT", "1")
+    assert_bit_identical(DiagnosticStencil(backend='cuda')(huge),
+                         oracle_output(DiagnosticStencil(backend='python'), huge))
+    assert_bit_identical(Jacobi3D(1.0, 0.25, backend='cuda')(tiny),
+                         oracle_output(Jacobi3D(1.0, 0.25, backend='python'), tiny))
+    monkeypatch.delenv("STENCIL_CUDA_STRICT")
+    # within the precondition the demoted arithmetic is exact: moderately large and small values
+    for scale in (1.0e30, 1.0e-30):
+        grid = (rng.uniform(0.5, 2.0, (8, 16, 128)) * scale).astype(numpy.float32)
+        assert_bit_identical(Jacobi3D(1.0, 0.25, backend='cuda')(grid),
+                             oracle_output(Jacobi3D(1.0, 0.25, backend='python'), grid))
+
+
+def test_apply_host_on_one_gpu_matches_oracle():
+    """SlabStencil.apply_host (pipelined host -> sweep -> host, the multi-GPU e2e path) at world 1,
+    followed by iterate(): oracle applied once, then three more times."""
+    import stencil_code_b200
+    from stencil_code_b200.backend.cuda.multi_gpu import SlabStencil
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    shape = (96, 256, 512)
+    window = stencil_code_b200.pinned_empty(shape)
+    window[...] = numpy.random.RandomState(5).random_sample(shape).astype(numpy.float32)
+    python_side = Jacobi3D(1.0, 0.25, backend='python')
+    with SlabStencil(Jacobi3D(1.0, 0.25), shape, world=1, rank=0) as slab:
+        assert slab.host_window() == (0, shape[0])
+        once = oracle_output(python_side, numpy.array(window), variant='c_parallel')
+        assert_bit_identical(numpy.array(slab.apply_host(window)), once)
+        slab.iterate(3)
+        expected = once
+        for _ in range(3):
+            expected = oracle_output(python_side, expected, variant='c_parallel')
+        assert_bit_identical(numpy.array(slab.result()), expected)
