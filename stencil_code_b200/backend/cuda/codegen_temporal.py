@@ -23,6 +23,7 @@ sweeps is the unchanged per-point program: results are bit-identical to two sepa
 Eligibility: rank 3, float32, exactly one grid argument, taps off the centre column only at
 dz = 0, |dz| <= 1, column radius <= 4, no data-indexed tables.
 """
+import math
 import os
 
 from ...stencil_exception import StencilException
@@ -124,7 +125,7 @@ def choose_config(program, device_props, second=None):
     best = None
     # measured on B200 (Jacobi-3D 512x1024x1024, GStencil/s): (16,2,8,p2) 977, (32,2,16,p1) 966,
     # (32,2,16,p2) 926-954; register blocks of 4 rows spill under the occupancy bound (355-377)
-    for MY, BY, NCW, prefetch in ((16, 2, 8, 2), (32, 2, 16, 1), (32, 2, 16, 2), (8, 1, 8, 2)):
+    for MY, BY, NCW, prefetch in ((16, 2, 8, 4), (16, 2, 8, 2), (32, 2, 16, 1), (32, 2, 16, 2), (8, 1, 8, 2)):
         if override:
             MY, BY, NCW = override.get("MY", MY), override.get("BY", BY), override.get("NCW", NCW)
             prefetch = override.get("prefetch", prefetch)
@@ -265,17 +266,27 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     e.close()
     e()
     # ------------------------------------------------------------------ consumers
+    # The loop body is emitted once per phase of lcm(W, S) phases: the register-window slot, the
+    # ring stage and the mid buffer of every access are then compile-time constants (immediate
+    # offsets of LDS/STS, no modulo arithmetic); only the mbarrier parity is carried.
+    P = W * S // math.gcd(W, S)
+    use_shfl = os.environ.get("STENCIL_CUDA_TEMPORAL_SHFL", "1") not in ("0", "")
     e("const int tr = warp;")
     e("const int gy = y0 + tr * {};               // first row of this thread's block".format(BY))
     e("const int gx = x0 + lane * 4;             // first column of this thread's block")
     e("const int sbase_in = ({} + tr * {}) * {} + {} + lane * 4;".format(HY, BY, PITCH, PADX))
     e("const int sbase_mid = tr * {} * {} + lane * 4;".format(BY, MP))
-    rows_needed = sorted({k[1] for k in fp.ages} |
-                         {b + _tap3(tap.offset)[1] for tap in second.taps() for b in range(BY)})
-    if clamp_rows:
-        for row in rows_needed:
-            e("const int rd{t} = min(max(gy + ({r}), 0), {n}) - (gy + ({r}));   // clamped row delta".format(
-                t=_tag(row), r=row, n=N1 - 1))
+    rows_in = sorted({k[1] for k in fp.ages})
+    rows_mid = sorted({b + _tap3(tap.offset)[1] for tap in second.taps() for b in range(BY)
+                       if _tap3(tap.offset)[0] == 0} | set(range(BY)))
+    # per-row base pointers (the clamped row offset of 'clamp' folded in): loads are pointer[immediate]
+    for row in rows_in:
+        delta = "(min(max(gy + ({r}), 0), {n}) - gy)".format(r=row, n=N1 - 1) if clamp_rows else "({})".format(row)
+        e("const float* const pI{t} = ring + sbase_in + {d} * {p};".format(t=_tag(row), d=delta, p=PITCH))
+    for row in rows_mid:
+        delta = "(min(max(gy + ({r}), 0), {n}) - gy)".format(r=row, n=N1 - 1) if clamp_rows else "({})".format(row)
+        e("const float* const pM{t} = mid + sbase_mid + {d} * {p};".format(t=_tag(row), d=delta, p=MP))
+    e("float* const mid_own_rows = mid + sbase_mid;")
     if clamp_cols:
         e("const bool x_edge = x0 <= 0 || x0 + {} > {};".format(128 + HX, N2))
     if not clamp:
@@ -311,6 +322,13 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     # which of this thread's outputs are inside the valid (interior) part of the mid tile and the grid
     lane_ok = "lane >= 1 && lane <= 30 && " if HX else ""
     e("const bool col_ok = {}gx >= 0 && gx < {};".format(lane_ok, N2))
+    for b in range(BY):
+        e("const bool store_ok{b} = col_ok && tr * {by} + {b} >= {hy} && tr * {by} + {b} < {hi} && "
+          "gy + {b} >= 0 && gy + {b} < {n1};".format(b=b, by=BY, hy=HY, hi=MY - HY, n1=N1))
+    e("float* dst = out + ((i64)u_begin * {} + gy) * {} + gx;   // this thread's block in the next output plane".format(
+        N1, domain.row_pitch))
+    if mirror:
+        e("const i64 mirror = out_peer ? (out_peer - out) + peer_shift : 0;")
     for (arg, index), ctype in sorted(const_refs.items()):
         e("const {} tc{}_{} = a{}[{}];".format(ctype, arg, index, arg, index))
     names = []
@@ -329,42 +347,45 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
         for c in sorted(c for c in names_by_col if c > (0 if in_quad else 3)):
             e("if (gx + {} > {}) {} = {};".format(c, N2 - 1, names_by_col[c], names_by_col[c - 1]))
 
-    def load_rows(pointer, pitch, by_row, name_of_col, declare):
-        """vectorised shared-memory loads of {row: cols} relative to the thread's block"""
+    def load_rows(prefix, offset, by_row, name_of_col, declare):
+        """vectorised shared-memory loads of {row: cols} through the per-row pointers ``prefix<row>``
+        at the compile-time offset ``offset`` (ring stage / mid buffer)"""
         for row in sorted(by_row):
+            pointer = "{}{}".format(prefix, _tag(row))
             for first, width, used in _group_loads(by_row[row]):
-                offset = "{}".format(row * pitch + first)
-                if clamp_rows:
-                    offset = "rd{} * {} + ({})".format(_tag(row), pitch, offset)
                 if width == 1:
-                    e("{}{} = {}[{}];".format(declare, name_of_col(row, used[0]), pointer, offset))
+                    e("{}{} = {}[{}];".format(declare, name_of_col(row, used[0]), pointer, offset + first))
                     continue
                 counter[0] += 1
                 tmp = "q{}".format(counter[0])
                 vec = "float4" if width == 4 else "float2"
-                e("const {v} {t} = *reinterpret_cast<const {v}*>({p} + ({o}));".format(v=vec, t=tmp, p=pointer, o=offset))
+                e("const {v} {t} = *reinterpret_cast<const {v}*>({p} + {o});".format(
+                    v=vec, t=tmp, p=pointer, o=offset + first))
                 e(" ".join("{}{} = {}.{};".format(declare, name_of_col(row, c), tmp, "xyzw"[c - first]) for c in used))
 
     e("int unit = 0;                        // newest streamed input plane, relative to p_first")
+    e("u32 par = 0;                         // parity of the ring's full barriers in this pass over the phases")
     e.open("while (true)")
-    for phase in range(W):
-        e("// ---- window phase {}".format(phase))
+    for phase in range(P):
+        stage = phase % S
+        e("// ---- phase {} (window slot {}, ring stage {}, mid buffer {})".format(phase, phase % W, stage, phase % 3))
         e("if (unit >= n_units) break;")
         e.open("")
-        e("mbar_wait(&bar_full[unit % {S}], (unit / {S}) & 1);".format(S=S))
+        fills = phase // S                       # how often this stage was filled before, within this pass
+        parity = "par" if fills % 2 == 0 else "(par ^ 1u)"
+        if (P // S) % 2 == 0:
+            parity = str(fills % 2)
+        e("mbar_wait(&bar_full[{}], {});".format(stage, parity))
         # ---------------- sweep-1 input window (same scheme as codegen_stream, regwin)
         reads = {}
         for key, ages in fp.ages.items():
             reads.setdefault(max(ages), []).append(key)
         for age in sorted(reads):
             back = 1 - age
-            e("const float* const uI{t} = ring + ((unit + {k} - {b}) % {S}) * {sf} + sbase_in;".format(
-                t=_tag(age), k=3 * S, b=back, S=S, sf=SF))
-        for age in sorted(reads):
             by_row = {}
             for (_, row, col) in reads[age]:
                 by_row.setdefault(row, set()).add(col)
-            load_rows("uI{}".format(_tag(age)), PITCH, by_row,
+            load_rows("pI", ((phase - back) % S) * SF, by_row,
                       lambda row, col, age=age: in_name(phase, age, row, col), "")
             if clamp_cols and any(c < 0 or c > 3 for cols in by_row.values() for c in cols):
                 e.open("if (x_edge)")
@@ -377,14 +398,14 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                 e.close()
         release_back = 1 - min(max(s) for s in fp.ages.values())
         e("__syncwarp();")
-        e("if (lane == 0 && unit >= {b}) mbar_arrive(&bar_empty[(unit - {b}) % {S}]);".format(b=release_back, S=S))
+        e("if (lane == 0 && unit >= {b}) mbar_arrive(&bar_empty[{s}]);".format(b=release_back, s=(phase - release_back) % S))
 
         # ---------------- sweep 1: mid plane zm = p_first + unit - 1
         e.open("if (unit >= 2)")
         e("const int zm = p_first + unit - 1;")
-        macc = [["ma{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
+        macc = [[mid_own(phase, 1, b, j) for j in range(4)] for b in range(BY)]     # straight into the window slot
         for b in range(BY):
-            e("float {};".format(", ".join(n + " = 0.0f" for n in macc[b])))
+            e(" ".join("{} = 0.0f;".format(n) for n in macc[b]))
         for statement in program.statements:
             for b in range(BY):
                 for j in range(4):
@@ -413,22 +434,33 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
             for b in range(BY):
                 column_fix({j: macc[b][j] for j in range(4)}, in_quad=True)
             e.close()
-        e("float* const mid_new = mid + (unit % 3) * {} + sbase_mid;".format(MF))
+        if clamp:
+            # axis-0 clamp of the intermediate grid, applied where a plane is produced (a uniform,
+            # rarely taken branch) instead of by two selects per point where it is used: the plane
+            # past the last one reads as the last one, the plane before the first one as the first
+            e.open("if (zm <= {} || zm > {})".format(c_lo[0], c_hi[0]))
+            e('asm volatile("" ::: "memory");          // keeps this a branch (not 2 selects per point)')
+            for b in range(BY):
+                for j in range(4):
+                    e("if (zm > {hi}) {new} = {prev}; else if (zm == {lo}) {prev} = {new};".format(
+                        hi=c_hi[0], lo=c_lo[0], new=mid_own(phase, 1, b, j), prev=mid_own(phase, 0, b, j)))
+            e.close()
         for b in range(BY):
-            for j in range(4):
-                e("{} = {};".format(mid_own(phase, 1, b, j), macc[b][j]))
-            e("*reinterpret_cast<float4*>(mid_new + {}) = make_float4({});".format(b * MP, ", ".join(macc[b])))
+            e("*reinterpret_cast<float4*>(mid_own_rows + {}) = make_float4({});".format(
+                (phase % 3) * MF + b * MP, ", ".join(macc[b])))
         e('asm volatile("bar.sync 1, {};" ::: "memory");'.format(NCW * 32))
 
         # ---------------- sweep 2: output plane zo = p_first + unit - 2
         e.open("if (unit >= 4)")
-        e("const int zo = p_first + unit - 2;")
-        e("const float* const uM = mid + ((unit + 2) % 3) * {} + sbase_mid;   // mid plane zo".format(MF))
+        mid_offset = ((phase + 2) % 3) * MF                    # buffer of mid plane zo
         # in-plane taps of sweep 2.  A tap in the point's own row and own quad is the thread's own
         # mid register.  Everything else is read from the mid buffer; under 'clamp' that includes
         # other rows of the thread's own block, because a block row outside the grid must read as
-        # the clamped row (the buffer read goes through the clamped row offset, a register would not)
+        # the clamped row (the buffer read goes through the clamped row pointer, a register would
+        # not).  Columns next to the quad in the point's own row come from the neighbouring lanes'
+        # registers by warp shuffle (no bank-conflicting scalar shared-memory loads).
         by_row = {}
+        shuffled = {}                     # (row, col) -> (source register of the neighbour lane, lane delta)
         for tap in second.taps():
             dz, dy, dx = _tap3(tap.offset)
             if dz != 0:
@@ -437,7 +469,11 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                 for j in range(4):
                     row, col = b + dy, j + dx
                     own = 0 <= col < 4 and (dy == 0 if clamp else 0 <= row < BY)
-                    if not own:
+                    if own:
+                        continue
+                    if use_shfl and dy == 0 and -4 <= col < 8:
+                        shuffled[(row, col)] = (mid_own(phase, 0, row, col % 4), -1 if col < 0 else 1)
+                    else:
                         by_row.setdefault(row, set()).add(col)
         if clamp_cols:
             for row, cols in by_row.items():       # the select cascade needs every column up to the quad
@@ -445,29 +481,42 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                     cols.update(range(min(cols), 0))
                 if max(cols) > 3:
                     cols.update(range(4, max(cols) + 1))
+        for key in [k for k in shuffled if k[1] in by_row.get(k[0], ())]:
+            del shuffled[key]                      # already read from the buffer for a tap in another row
+        if clamp_cols:
+            for (row, col) in list(shuffled):
+                span = range(col, 0) if col < 0 else range(4, col + 1)
+                for c in span:
+                    if (row, c) not in shuffled and c not in by_row.get(row, ()):
+                        shuffled[(row, c)] = (mid_own(phase, 0, row, c % 4), -1 if c < 0 else 1)
 
         def nb_name(row, col, same_row=False):
             own = 0 <= col < 4 and (same_row if clamp else 0 <= row < BY)
             if own:
                 return mid_own(phase, 0, row, col)
             return "n_{}_{}".format(_tag(row), _tag(col))
-        load_rows("uM", MP, by_row, nb_name, "float ")
-        if clamp_cols and any(c < 0 or c > 3 for cols in by_row.values() for c in cols):
+        load_rows("pM", mid_offset, by_row, nb_name, "float ")
+        for (row, col), (source, delta) in sorted(shuffled.items()):
+            e("float n_{}_{} = __shfl_{}_sync(0xffffffffu, {}, 1);".format(
+                _tag(row), _tag(col), "up" if delta < 0 else "down", source))
+        outer_rows = {}
+        for row, cols in by_row.items():
+            outer_rows.setdefault(row, set()).update(c for c in cols if c < 0 or c > 3)
+        for (row, col) in shuffled:
+            outer_rows.setdefault(row, set()).add(col)
+        if clamp_cols and any(outer_rows.values()):
             e.open("if (x_edge)")
-            for row in sorted(by_row):
-                outer = [c for c in by_row[row] if c < 0 or c > 3]
+            for row in sorted(outer_rows):
+                outer = sorted(outer_rows[row])
                 if outer:
                     # the cascade starts from the thread's own quad: columns 0 and 3 of this row,
                     # loaded from the buffer if the row is not the point's own, else the register
                     names = {c: nb_name(row, c) for c in outer}
                     for c in (0, 3):
-                        names[c] = ("n_{}_{}".format(_tag(row), c) if c in by_row[row]
+                        names[c] = ("n_{}_{}".format(_tag(row), c) if c in by_row.get(row, ())
                                     else mid_own(phase, 0, row, c))
                     column_fix(names)
             e.close()
-        if clamp:
-            e("const bool z_lo = zo - 1 < {};   // axis-0 clamp of the intermediate grid".format(c_lo[0]))
-            e("const bool z_hi = zo + 1 > {};".format(c_hi[0]))
         acc = [["acc{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
         for b in range(BY):
             e("float {};".format(", ".join(n + " = 0.0f" for n in acc[b])))
@@ -478,14 +527,12 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                         dz, dy, dx = _tap3(tap.offset)
                         if dz == 0:
                             return nb_name(b + dy, j + dx, same_row=(dy == 0))
-                        own = mid_own(phase, dz, b, j)
-                        if clamp:
-                            return "({} ? {} : {})".format("z_lo" if dz < 0 else "z_hi", mid_own(phase, 0, b, j), own)
-                        return own
+                        return mid_own(phase, dz, b, j)
                     single = pp.PointProgram(3, shape, second.out_ctype, second.args, [statement],
                                              second.ghost_depth, boundary)
                     e(emit_statements(single, tap_text, table_text, acc=acc[b][j], indent="")[0])
         if not clamp:
+            e("const int zo = p_first + unit - 2;")
             mask2 = "halo_mask2" if two_masks else "halo_mask"
             ztests = []
             if j_lo[0] > 0:
@@ -501,18 +548,18 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                     e("if (zo_halo || ({} & {}u)) {} = {};".format(mask2, 1 << (b * 4 + j), acc[b][j], value))
             e.close()
         for b in range(BY):
-            row_ok = "tr * {by} + {b} >= {hy} && tr * {by} + {b} < {hi} && gy + {b} >= 0 && gy + {b} < {n1}".format(
-                by=BY, b=b, hy=HY, hi=MY - HY, n1=N1)
-            e.open("if (col_ok && {})".format(row_ok))
-            e("float* const dst = out + ((i64)zo * {} + (gy + {})) * {} + gx;".format(N1, b, domain.row_pitch))
-            e("st_global_v4(dst, {});".format(", ".join(acc[b])))
+            e.open("if (store_ok{})".format(b))
+            e("st_global_v4(dst + {}, {});".format(b * domain.row_pitch, ", ".join(acc[b])))
             if mirror:                  # slab boundary launches also fill the neighbour's ghost planes
-                e("if (out_peer) st_global_v4(out_peer + (dst - out) + peer_shift, {});".format(", ".join(acc[b])))
+                e("if (out_peer) st_global_v4(dst + {} + mirror, {});".format(b * domain.row_pitch, ", ".join(acc[b])))
             e.close()
+        e("dst += {};".format(N1 * domain.row_pitch))
         e.close()   # unit >= 4
         e.close()   # unit >= 2
         e("++unit;")
         e.close()
+    if (P // S) % 2 == 1:
+        e("par ^= 1u;")
     e.close()   # while
     e.close()   # kernel
     return e.text()
