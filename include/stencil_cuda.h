@@ -130,6 +130,17 @@ int         sc_launch_pingpong(sc_module* module, const char* function,
  * griddepcontrol.wait before they touch memory the preceding launch writes or reads            */
 #define SC_LAUNCH_PROGRAMMATIC 1u
 
+/* As sc_launch_pingpong, for kernels that take the number of the step they perform as a 32-bit
+ * parameter: launch i receives `first_step + i` in parameter `step_arg` (an index into the args
+ * arrays; the pointed-to uint32_t of both blocks is overwritten).  Used by the slab-decomposed
+ * iterated sweeps (multi-GPU): every launch is one exchange step whose boundary CTAs wait for /
+ * publish the step number in flag words in the neighbouring GPUs' memory, so a whole run of
+ * steps is enqueued by one call and the GPUs synchronise among themselves.                      */
+int         sc_launch_steps(sc_module* module, const char* function,
+                            const uint32_t grid[3], const uint32_t block[3], uint32_t dynamic_smem,
+                            void* stream, void** args_even, void** args_odd, int count,
+                            uint32_t flags, int step_arg, uint32_t first_step);
+
 /* ---- streams and events --------------------------------------------------------------------- */
 int         sc_stream_create(void** stream);
 int         sc_stream_destroy(void* stream);

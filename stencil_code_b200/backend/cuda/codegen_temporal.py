@@ -164,13 +164,36 @@ def choose_config(program, device_props, second=None):
     return best
 
 
+STEP_HELPERS = r'''
+__device__ __forceinline__ u32 ld_acquire_sys(const u32* p) {
+    u32 v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(u32* p, u32 v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+'''
+
+
 def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True, second=None,
-             second_domain=None):
+             second_domain=None, step_kernel=False):
     """CUDA source of the fused kernel.  ``mirror``: also store results through ``out_peer`` (slab
     boundary launches); defaults to ``domain.is_slab``.  ``second``: the program of the second
     sweep when it is another stencil than the first (``fuse(a, b)``); its halo (``zero``/``copy``)
-    follows ``second_domain``, i.e. its own ghost depth."""
+    follows ``second_domain``, i.e. its own ghost depth.
+
+    ``step_kernel``: ONE launch per exchange step of a slab (``multi_gpu.SlabStencil``).  The
+    grid's first z-slices are the boundary planes next to each neighbouring slab -- scheduled
+    first; they wait (the producer's elected thread, ``ld.acquire.sys``) until the neighbour's flag
+    says its previous step's boundary planes are in this slab's ghost planes, store their results
+    locally and into the neighbour's ghost planes (peer memory over NVLink), and the last of them
+    to finish publishes this slab's flag in the neighbours' memory (``st.release.sys`` after a
+    system-scope fence).  The remaining z-slices are the interior chunks, which never touch ghost
+    planes: they hide the exchange."""
     mirror = domain.is_slab if mirror is None else mirror
+    if step_kernel:
+        mirror = True
     second = program if second is None else second
     second_domain = domain if second_domain is None else second_domain
     shape = program.shape
@@ -214,8 +237,16 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     e("// temporal strategy: two fused sweeps | grid {} boundary {} | mid tile {}x128, output {}x{}, "
       "BY={} ring S={}".format(shape, boundary, MY, cfg.OUT_ROWS, cfg.OUT_COLS, BY, S))
     params = ["const {}* __restrict__ a{}".format(arg.ctype, arg.index) for arg in program.args]
-    params += ["const __grid_constant__ TensorMap tm0", "float* __restrict__ out",
-               "float* __restrict__ out_peer", "i64 peer_shift", "int a0_begin", "int a0_end", "int chunk_len"]
+    if step_kernel:
+        e.lines.append(STEP_HELPERS)
+        params += ["const __grid_constant__ TensorMap tm0", "float* __restrict__ out",
+                   "int a0_begin", "int a0_end", "int chunk_len",
+                   "float* __restrict__ peer_up", "i64 shift_up", "float* __restrict__ peer_dn", "i64 shift_dn",
+                   "int top_begin", "int top_end", "int bot_begin", "int bot_end",
+                   "u32* sync", "u32* flag_up", "u32* flag_dn", "u32 step"]
+    else:
+        params += ["const __grid_constant__ TensorMap tm0", "float* __restrict__ out",
+                   "float* __restrict__ out_peer", "i64 peer_shift", "int a0_begin", "int a0_end", "int chunk_len"]
     e('extern "C" __global__ void __launch_bounds__({}, {})'.format(cfg.threads, cfg.blocks_per_sm))
     e("{}({})".format(function, ", ".join(params)))
     e.open("")
@@ -231,8 +262,31 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     e("const int x0 = blockIdx.x * {} - {};     // origin of the mid tile (outputs are its interior)".format(
         cfg.OUT_COLS, PADX))
     e("const int y0 = blockIdx.y * {} - {};".format(cfg.OUT_ROWS, HY))
-    e("const int u_begin = a0_begin + blockIdx.z * chunk_len;")
-    e("const int u_end = min(u_begin + chunk_len, a0_end);")
+    n_edge = int(domain.open_lo) + int(domain.open_hi) if step_kernel else 0
+    if step_kernel:
+        e("// z-slices: boundary planes first ({} neighbour{}), then the interior chunks".format(
+            n_edge, "" if n_edge == 1 else "s"))
+        e("int u_begin, u_end;")
+        e("float* out_peer = nullptr; i64 peer_shift = 0; const u32* wait_flag = nullptr;")
+        e("const bool edge = blockIdx.z < {};".format(n_edge))
+        first = True
+        if domain.open_lo:
+            e.open("if (blockIdx.z == 0)")
+            e("u_begin = top_begin; u_end = top_end; out_peer = peer_up; peer_shift = shift_up; wait_flag = sync;")
+            e.close()
+            first = False
+        if domain.open_hi:
+            e.open("{}if (blockIdx.z == {})".format("" if first else "else ", 0 if first else 1))
+            e("u_begin = bot_begin; u_end = bot_end; out_peer = peer_dn; peer_shift = shift_dn; wait_flag = sync + 1;")
+            e.close()
+            first = False
+        e.open("{}".format("" if first else "else"))
+        e("u_begin = a0_begin + ((int)blockIdx.z - {}) * chunk_len;".format(n_edge))
+        e("u_end = min(u_begin + chunk_len, a0_end);")
+        e.close()
+    else:
+        e("const int u_begin = a0_begin + blockIdx.z * chunk_len;")
+        e("const int u_end = min(u_begin + chunk_len, a0_end);")
     e("if (u_begin >= u_end) return;")
     e("const int p_first = u_begin - 2;             // axis-0 index of streamed input plane 0")
     e("const int n_units = (u_end - u_begin) + 4;")
@@ -249,6 +303,13 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     # ------------------------------------------------------------------ producer
     e.open("if (warp == {})".format(NCW))
     e("if (lane == 0) tma_prefetch_desc(&tm0);")
+    if step_kernel:
+        e("// boundary planes read ghost planes: the neighbour's previous step must have delivered them")
+        e("// (and have finished reading the ghost planes this step overwrites in ITS memory)")
+        e.open("if (edge && lane == 0)")
+        e("while (ld_acquire_sys(wait_flag) < step) { }")
+        e.close()
+        e("__syncwarp();")
     e.open("for (int k = 0; k < n_units; ++k)")
     e("const int s = k % {};".format(S))
     e("if (k >= {S}) mbar_wait(&bar_empty[s], ((k / {S}) - 1) & 1);".format(S=S))
@@ -271,6 +332,9 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     # offsets of LDS/STS, no modulo arithmetic); only the mbarrier parity is carried.
     P = W * S // math.gcd(W, S)
     use_shfl = os.environ.get("STENCIL_CUDA_TEMPORAL_SHFL", "1") not in ("0", "")
+    in_shfl = os.environ.get("STENCIL_CUDA_TEMPORAL_INSHFL", "1") not in ("0", "")
+    own_regs = os.environ.get("STENCIL_CUDA_TEMPORAL_OWNREGS", "1") not in ("0", "")
+    own_in_block = own_regs or not (clamp and HY > 0)       # sweep 2 reads own-block rows from registers
     e("const int tr = warp;")
     e("const int gy = y0 + tr * {};               // first row of this thread's block".format(BY))
     e("const int gx = x0 + lane * 4;             // first column of this thread's block")
@@ -289,6 +353,11 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     e("float* const mid_own_rows = mid + sbase_mid;")
     if clamp_cols:
         e("const bool x_edge = x0 <= 0 || x0 + {} > {};".format(128 + HX, N2))
+    if clamp_rows and own_regs and BY > 1:
+        e("const bool y_edge = y0 < 0 || y0 + {} > {};".format(MY, N1))
+        for b in range(BY):
+            e("const int cr{b} = min(max(gy + {b}, 0), {n}) - gy;   // block row that row {b} reads as under 'clamp'".format(
+                b=b, n=N1 - 1))
     if not clamp:
         e("u32 halo_mask = 0;                   // bit (b*4+j): the point lies in the in-plane halo")
         for b in range(BY):
@@ -363,204 +432,258 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                     v=vec, t=tmp, p=pointer, o=offset + first))
                 e(" ".join("{}{} = {}.{};".format(declare, name_of_col(row, c), tmp, "xyzw"[c - first]) for c in used))
 
-    e("int unit = 0;                        // newest streamed input plane, relative to p_first")
-    e("u32 par = 0;                         // parity of the ring's full barriers in this pass over the phases")
-    e.open("while (true)")
-    for phase in range(P):
-        stage = phase % S
-        e("// ---- phase {} (window slot {}, ring stage {}, mid buffer {})".format(phase, phase % W, stage, phase % 3))
-        e("if (unit >= n_units) break;")
-        e.open("")
-        fills = phase // S                       # how often this stage was filled before, within this pass
-        parity = "par" if fills % 2 == 0 else "(par ^ 1u)"
-        if (P // S) % 2 == 0:
-            parity = str(fills % 2)
-        e("mbar_wait(&bar_full[{}], {});".format(stage, parity))
-        # ---------------- sweep-1 input window (same scheme as codegen_stream, regwin)
-        reads = {}
-        for key, ages in fp.ages.items():
-            reads.setdefault(max(ages), []).append(key)
-        for age in sorted(reads):
-            back = 1 - age
-            by_row = {}
-            for (_, row, col) in reads[age]:
-                by_row.setdefault(row, set()).add(col)
-            load_rows("pI", ((phase - back) % S) * SF, by_row,
-                      lambda row, col, age=age: in_name(phase, age, row, col), "")
-            if clamp_cols and any(c < 0 or c > 3 for cols in by_row.values() for c in cols):
-                e.open("if (x_edge)")
-                for row in sorted(by_row):
-                    outer = [c for c in by_row[row] if c < 0 or c > 3]
-                    if outer:
-                        span = range(min(min(outer), 0), max(max(outer), 3) + 1)
-                        column_fix({c: in_name(phase, age, row, c) for c in span if (0, row, c) in fp.ages},
-                                   in_quad=fp.ragged)
-                e.close()
-        release_back = 1 - min(max(s) for s in fp.ages.values())
-        e("__syncwarp();")
-        e("if (lane == 0 && unit >= {b}) mbar_arrive(&bar_empty[{s}]);".format(b=release_back, s=(phase - release_back) % S))
-
-        # ---------------- sweep 1: mid plane zm = p_first + unit - 1
-        e.open("if (unit >= 2)")
-        e("const int zm = p_first + unit - 1;")
-        macc = [[mid_own(phase, 1, b, j) for j in range(4)] for b in range(BY)]     # straight into the window slot
-        for b in range(BY):
-            e(" ".join("{} = 0.0f;".format(n) for n in macc[b]))
-        for statement in program.statements:
-            for b in range(BY):
-                for j in range(4):
-                    def tap_text(tap, b=b, j=j):
-                        dz, dy, dx = _tap3(tap.offset)
-                        return in_name(phase, dz, b + dy, j + dx)
-                    single = pp.PointProgram(3, shape, program.out_ctype, program.args, [statement],
-                                             program.ghost_depth, boundary)
-                    e(emit_statements(single, tap_text, table_text, acc=macc[b][j], indent="")[0])
-        if not clamp:
-            ztests = []
-            if i_lo[0] > 0:
-                ztests.append("zm < {}".format(i_lo[0]))
-            if i_hi[0] < N0:
-                ztests.append("zm >= {}".format(i_hi[0]))
-            e("const bool zm_halo = {};".format(" || ".join(ztests) if ztests else "false"))
-            e.open("if (zm_halo || halo_mask)")
-            for b in range(BY):
-                for j in range(4):
-                    value = in_name(phase, 0, b, j) if copy else "0.0f"
-                    e("if (zm_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), macc[b][j], value))
-            e.close()
-        if clamp_cols and fp.ragged:
-            # the intermediate grid's columns past the last one read as the last one
-            e.open("if (x_edge)")
-            for b in range(BY):
-                column_fix({j: macc[b][j] for j in range(4)}, in_quad=True)
-            e.close()
-        if clamp:
-            # axis-0 clamp of the intermediate grid, applied where a plane is produced (a uniform,
-            # rarely taken branch) instead of by two selects per point where it is used: the plane
-            # past the last one reads as the last one, the plane before the first one as the first
-            e.open("if (zm <= {} || zm > {})".format(c_lo[0], c_hi[0]))
-            e('asm volatile("" ::: "memory");          // keeps this a branch (not 2 selects per point)')
-            for b in range(BY):
-                for j in range(4):
-                    e("if (zm > {hi}) {new} = {prev}; else if (zm == {lo}) {prev} = {new};".format(
-                        hi=c_hi[0], lo=c_lo[0], new=mid_own(phase, 1, b, j), prev=mid_own(phase, 0, b, j)))
-            e.close()
-        for b in range(BY):
-            e("*reinterpret_cast<float4*>(mid_own_rows + {}) = make_float4({});".format(
-                (phase % 3) * MF + b * MP, ", ".join(macc[b])))
-        e('asm volatile("bar.sync 1, {};" ::: "memory");'.format(NCW * 32))
-
-        # ---------------- sweep 2: output plane zo = p_first + unit - 2
-        e.open("if (unit >= 4)")
-        mid_offset = ((phase + 2) % 3) * MF                    # buffer of mid plane zo
-        # in-plane taps of sweep 2.  A tap in the point's own row and own quad is the thread's own
-        # mid register.  Everything else is read from the mid buffer; under 'clamp' that includes
-        # other rows of the thread's own block, because a block row outside the grid must read as
-        # the clamped row (the buffer read goes through the clamped row pointer, a register would
-        # not).  Columns next to the quad in the point's own row come from the neighbouring lanes'
-        # registers by warp shuffle (no bank-conflicting scalar shared-memory loads).
-        by_row = {}
-        shuffled = {}                     # (row, col) -> (source register of the neighbour lane, lane delta)
-        for tap in second.taps():
-            dz, dy, dx = _tap3(tap.offset)
-            if dz != 0:
-                continue
-            for b in range(BY):
-                for j in range(4):
-                    row, col = b + dy, j + dx
-                    own = 0 <= col < 4 and (dy == 0 if clamp else 0 <= row < BY)
-                    if own:
-                        continue
-                    if use_shfl and dy == 0 and -4 <= col < 8:
-                        shuffled[(row, col)] = (mid_own(phase, 0, row, col % 4), -1 if col < 0 else 1)
+    def emit_loop(mirror):
+        """the consumers' plane loop; ``mirror``: results also go to the neighbour's ghost planes"""
+        e("int unit = 0;                        // newest streamed input plane, relative to p_first")
+        e("u32 par = 0;                         // parity of the ring's full barriers in this pass over the phases")
+        e.open("while (true)")
+        for phase in range(P):
+            stage = phase % S
+            e("// ---- phase {} (window slot {}, ring stage {}, mid buffer {})".format(phase, phase % W, stage, phase % 3))
+            e("if (unit >= n_units) break;")
+            e.open("")
+            fills = phase // S                       # how often this stage was filled before, within this pass
+            parity = "par" if fills % 2 == 0 else "(par ^ 1u)"
+            if (P // S) % 2 == 0:
+                parity = str(fills % 2)
+            e("mbar_wait(&bar_full[{}], {});".format(stage, parity))
+            # ---------------- sweep-1 input window (same scheme as codegen_stream, regwin)
+            reads = {}
+            for key, ages in fp.ages.items():
+                reads.setdefault(max(ages), []).append(key)
+            for age in sorted(reads):
+                back = 1 - age
+                by_row, lane_edge = {}, {}
+                for (_, row, col) in reads[age]:
+                    source = fp.ages.get((0, row, col % 4))
+                    if in_shfl and (col < 0 or col > 3) and -4 <= col < 8 and source and min(source) <= age <= max(source):
+                        lane_edge.setdefault(row, set()).add(col)
                     else:
                         by_row.setdefault(row, set()).add(col)
-        if clamp_cols:
-            for row, cols in by_row.items():       # the select cascade needs every column up to the quad
-                if min(cols) < 0:
-                    cols.update(range(min(cols), 0))
-                if max(cols) > 3:
-                    cols.update(range(4, max(cols) + 1))
-        for key in [k for k in shuffled if k[1] in by_row.get(k[0], ())]:
-            del shuffled[key]                      # already read from the buffer for a tap in another row
-        if clamp_cols:
-            for (row, col) in list(shuffled):
-                span = range(col, 0) if col < 0 else range(4, col + 1)
-                for c in span:
-                    if (row, c) not in shuffled and c not in by_row.get(row, ()):
-                        shuffled[(row, c)] = (mid_own(phase, 0, row, c % 4), -1 if c < 0 else 1)
+                load_rows("pI", ((phase - back) % S) * SF, by_row,
+                          lambda row, col, age=age: in_name(phase, age, row, col), "")
+                # columns next to the quad: the neighbouring lane holds them in its window registers.
+                # Only the warp's first / last lane reads shared memory (the tile's column halo): one
+                # conflict-free wavefront instead of a four-way bank conflict per value.
+                for row in sorted(lane_edge):
+                    offset = ((phase - back) % S) * SF
+                    for col in sorted(lane_edge[row]):
+                        left = col < 0
+                        name = in_name(phase, age, row, col)
+                        e("{n} = __shfl_{d}_sync(0xffffffffu, {src}, 1);".format(
+                            n=name, d="up" if left else "down", src=in_name(phase, age, row, col % 4)))
+                        e("if (lane == {l}) {n} = pI{t}[{o}];".format(l=0 if left else 31, n=name, t=_tag(row), o=offset + col))
+                for row, cols in lane_edge.items():
+                    by_row.setdefault(row, set()).update(cols)         # for the column cascade below
+                if clamp_cols and any(c < 0 or c > 3 for cols in by_row.values() for c in cols):
+                    e.open("if (x_edge)")
+                    for row in sorted(by_row):
+                        outer = [c for c in by_row[row] if c < 0 or c > 3]
+                        if outer:
+                            span = range(min(min(outer), 0), max(max(outer), 3) + 1)
+                            column_fix({c: in_name(phase, age, row, c) for c in span if (0, row, c) in fp.ages},
+                                       in_quad=fp.ragged)
+                    e.close()
+            release_back = 1 - min(max(s) for s in fp.ages.values())
+            e("__syncwarp();")
+            e("if (lane == 0 && unit >= {b}) mbar_arrive(&bar_empty[{s}]);".format(b=release_back, s=(phase - release_back) % S))
 
-        def nb_name(row, col, same_row=False):
-            own = 0 <= col < 4 and (same_row if clamp else 0 <= row < BY)
-            if own:
-                return mid_own(phase, 0, row, col)
-            return "n_{}_{}".format(_tag(row), _tag(col))
-        load_rows("pM", mid_offset, by_row, nb_name, "float ")
-        for (row, col), (source, delta) in sorted(shuffled.items()):
-            e("float n_{}_{} = __shfl_{}_sync(0xffffffffu, {}, 1);".format(
-                _tag(row), _tag(col), "up" if delta < 0 else "down", source))
-        outer_rows = {}
-        for row, cols in by_row.items():
-            outer_rows.setdefault(row, set()).update(c for c in cols if c < 0 or c > 3)
-        for (row, col) in shuffled:
-            outer_rows.setdefault(row, set()).add(col)
-        if clamp_cols and any(outer_rows.values()):
-            e.open("if (x_edge)")
-            for row in sorted(outer_rows):
-                outer = sorted(outer_rows[row])
-                if outer:
-                    # the cascade starts from the thread's own quad: columns 0 and 3 of this row,
-                    # loaded from the buffer if the row is not the point's own, else the register
-                    names = {c: nb_name(row, c) for c in outer}
-                    for c in (0, 3):
-                        names[c] = ("n_{}_{}".format(_tag(row), c) if c in by_row.get(row, ())
-                                    else mid_own(phase, 0, row, c))
-                    column_fix(names)
-            e.close()
-        acc = [["acc{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
-        for b in range(BY):
-            e("float {};".format(", ".join(n + " = 0.0f" for n in acc[b])))
-        for statement in second.statements:
+            # ---------------- sweep 1: mid plane zm = p_first + unit - 1
+            e.open("if (unit >= 2)")
+            e("const int zm = p_first + unit - 1;")
+            macc = [[mid_own(phase, 1, b, j) for j in range(4)] for b in range(BY)]     # straight into the window slot
             for b in range(BY):
-                for j in range(4):
-                    def tap_text(tap, b=b, j=j):
-                        dz, dy, dx = _tap3(tap.offset)
-                        if dz == 0:
-                            return nb_name(b + dy, j + dx, same_row=(dy == 0))
-                        return mid_own(phase, dz, b, j)
-                    single = pp.PointProgram(3, shape, second.out_ctype, second.args, [statement],
-                                             second.ghost_depth, boundary)
-                    e(emit_statements(single, tap_text, table_text, acc=acc[b][j], indent="")[0])
-        if not clamp:
-            e("const int zo = p_first + unit - 2;")
-            mask2 = "halo_mask2" if two_masks else "halo_mask"
-            ztests = []
-            if j_lo[0] > 0:
-                ztests.append("zo < {}".format(j_lo[0]))
-            if j_hi[0] < N0:
-                ztests.append("zo >= {}".format(j_hi[0]))
-            e("const bool zo_halo = {};".format(" || ".join(ztests) if ztests else "false"))
-            e.open("if (zo_halo || {})".format(mask2))
+                e(" ".join("{} = 0.0f;".format(n) for n in macc[b]))
+            for statement in program.statements:
+                for b in range(BY):
+                    for j in range(4):
+                        def tap_text(tap, b=b, j=j):
+                            dz, dy, dx = _tap3(tap.offset)
+                            return in_name(phase, dz, b + dy, j + dx)
+                        single = pp.PointProgram(3, shape, program.out_ctype, program.args, [statement],
+                                                 program.ghost_depth, boundary)
+                        e(emit_statements(single, tap_text, table_text, acc=macc[b][j], indent="")[0])
+            if not clamp:
+                ztests = []
+                if i_lo[0] > 0:
+                    ztests.append("zm < {}".format(i_lo[0]))
+                if i_hi[0] < N0:
+                    ztests.append("zm >= {}".format(i_hi[0]))
+                e("const bool zm_halo = {};".format(" || ".join(ztests) if ztests else "false"))
+                e.open("if (zm_halo || halo_mask)")
+                for b in range(BY):
+                    for j in range(4):
+                        value = in_name(phase, 0, b, j) if copy else "0.0f"
+                        e("if (zm_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), macc[b][j], value))
+                e.close()
+            if clamp_cols and fp.ragged:
+                # the intermediate grid's columns past the last one read as the last one
+                e.open("if (x_edge)")
+                for b in range(BY):
+                    column_fix({j: macc[b][j] for j in range(4)}, in_quad=True)
+                e.close()
+            if clamp_rows and own_regs and BY > 1:
+                # rows of the thread's own block that lie outside the grid read as the clamped row: where
+                # that row is in the same block, copy it now (a uniform branch, taken by edge tiles only),
+                # so that sweep 2 can take own-block rows from registers instead of shared memory
+                e.open("if (y_edge)")
+                e('asm volatile("" ::: "memory");')
+                for b in range(BY):
+                    for c in range(BY):
+                        if c != b:
+                            e("if (cr{} == {}) {{ {} }}".format(b, c, " ".join(
+                                "{} = {};".format(mid_own(phase, 1, b, j), mid_own(phase, 1, c, j)) for j in range(4))))
+                e.close()
+            if clamp:
+                # axis-0 clamp of the intermediate grid, applied where a plane is produced (a uniform,
+                # rarely taken branch) instead of by two selects per point where it is used: the plane
+                # past the last one reads as the last one, the plane before the first one as the first
+                e.open("if (zm <= {} || zm > {})".format(c_lo[0], c_hi[0]))
+                e('asm volatile("" ::: "memory");          // keeps this a branch (not 2 selects per point)')
+                for b in range(BY):
+                    for j in range(4):
+                        e("if (zm > {hi}) {new} = {prev}; else if (zm == {lo}) {prev} = {new};".format(
+                            hi=c_hi[0], lo=c_lo[0], new=mid_own(phase, 1, b, j), prev=mid_own(phase, 0, b, j)))
+                e.close()
             for b in range(BY):
-                for j in range(4):
-                    # 'copy': the halo of sweep 2 copies the halo of mid, which copied the input
-                    value = mid_own(phase, 0, b, j) if copy else "0.0f"
-                    e("if (zo_halo || ({} & {}u)) {} = {};".format(mask2, 1 << (b * 4 + j), acc[b][j], value))
+                e("*reinterpret_cast<float4*>(mid_own_rows + {}) = make_float4({});".format(
+                    (phase % 3) * MF + b * MP, ", ".join(macc[b])))
+            e('asm volatile("bar.sync 1, {};" ::: "memory");'.format(NCW * 32))
+
+            # ---------------- sweep 2: output plane zo = p_first + unit - 2
+            e.open("if (unit >= 4)")
+            mid_offset = ((phase + 2) % 3) * MF                    # buffer of mid plane zo
+            # in-plane taps of sweep 2.  A tap in the point's own row and own quad is the thread's own
+            # mid register.  Everything else is read from the mid buffer; under 'clamp' that includes
+            # other rows of the thread's own block, because a block row outside the grid must read as
+            # the clamped row (the buffer read goes through the clamped row pointer, a register would
+            # not).  Columns next to the quad in the point's own row come from the neighbouring lanes'
+            # registers by warp shuffle (no bank-conflicting scalar shared-memory loads).
+            by_row = {}
+            shuffled = {}                     # (row, col) -> (source register of the neighbour lane, lane delta)
+            for tap in second.taps():
+                dz, dy, dx = _tap3(tap.offset)
+                if dz != 0:
+                    continue
+                for b in range(BY):
+                    for j in range(4):
+                        row, col = b + dy, j + dx
+                        own = 0 <= col < 4 and (dy == 0 if (clamp and not own_in_block) else 0 <= row < BY)
+                        if own:
+                            continue
+                        if use_shfl and dy == 0 and -4 <= col < 8:
+                            shuffled[(row, col)] = (mid_own(phase, 0, row, col % 4), -1 if col < 0 else 1)
+                        else:
+                            by_row.setdefault(row, set()).add(col)
+            if clamp_cols:
+                for row, cols in by_row.items():       # the select cascade needs every column up to the quad
+                    if min(cols) < 0:
+                        cols.update(range(min(cols), 0))
+                    if max(cols) > 3:
+                        cols.update(range(4, max(cols) + 1))
+            for key in [k for k in shuffled if k[1] in by_row.get(k[0], ())]:
+                del shuffled[key]                      # already read from the buffer for a tap in another row
+            if clamp_cols:
+                for (row, col) in list(shuffled):
+                    span = range(col, 0) if col < 0 else range(4, col + 1)
+                    for c in span:
+                        if (row, c) not in shuffled and c not in by_row.get(row, ()):
+                            shuffled[(row, c)] = (mid_own(phase, 0, row, c % 4), -1 if c < 0 else 1)
+
+            def nb_name(row, col, same_row=False):
+                own = 0 <= col < 4 and (same_row if (clamp and not own_in_block) else 0 <= row < BY)
+                if own:
+                    return mid_own(phase, 0, row, col)
+                return "n_{}_{}".format(_tag(row), _tag(col))
+            load_rows("pM", mid_offset, by_row, nb_name, "float ")
+            for (row, col), (source, delta) in sorted(shuffled.items()):
+                e("float n_{}_{} = __shfl_{}_sync(0xffffffffu, {}, 1);".format(
+                    _tag(row), _tag(col), "up" if delta < 0 else "down", source))
+            outer_rows = {}
+            for row, cols in by_row.items():
+                outer_rows.setdefault(row, set()).update(c for c in cols if c < 0 or c > 3)
+            for (row, col) in shuffled:
+                outer_rows.setdefault(row, set()).add(col)
+            if clamp_cols and any(outer_rows.values()):
+                e.open("if (x_edge)")
+                for row in sorted(outer_rows):
+                    outer = sorted(outer_rows[row])
+                    if outer:
+                        # the cascade starts from the thread's own quad: columns 0 and 3 of this row,
+                        # loaded from the buffer if the row is not the point's own, else the register
+                        names = {c: nb_name(row, c) for c in outer}
+                        for c in (0, 3):
+                            names[c] = ("n_{}_{}".format(_tag(row), c) if c in by_row.get(row, ())
+                                        else mid_own(phase, 0, row, c))
+                        column_fix(names)
+                e.close()
+            acc = [["acc{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
+            for b in range(BY):
+                e("float {};".format(", ".join(n + " = 0.0f" for n in acc[b])))
+            for statement in second.statements:
+                for b in range(BY):
+                    for j in range(4):
+                        def tap_text(tap, b=b, j=j):
+                            dz, dy, dx = _tap3(tap.offset)
+                            if dz == 0:
+                                return nb_name(b + dy, j + dx, same_row=(dy == 0))
+                            return mid_own(phase, dz, b, j)
+                        single = pp.PointProgram(3, shape, second.out_ctype, second.args, [statement],
+                                                 second.ghost_depth, boundary)
+                        e(emit_statements(single, tap_text, table_text, acc=acc[b][j], indent="")[0])
+            if not clamp:
+                e("const int zo = p_first + unit - 2;")
+                mask2 = "halo_mask2" if two_masks else "halo_mask"
+                ztests = []
+                if j_lo[0] > 0:
+                    ztests.append("zo < {}".format(j_lo[0]))
+                if j_hi[0] < N0:
+                    ztests.append("zo >= {}".format(j_hi[0]))
+                e("const bool zo_halo = {};".format(" || ".join(ztests) if ztests else "false"))
+                e.open("if (zo_halo || {})".format(mask2))
+                for b in range(BY):
+                    for j in range(4):
+                        # 'copy': the halo of sweep 2 copies the halo of mid, which copied the input
+                        value = mid_own(phase, 0, b, j) if copy else "0.0f"
+                        e("if (zo_halo || ({} & {}u)) {} = {};".format(mask2, 1 << (b * 4 + j), acc[b][j], value))
+                e.close()
+            for b in range(BY):
+                e.open("if (store_ok{})".format(b))
+                e("st_global_v4(dst + {}, {});".format(b * domain.row_pitch, ", ".join(acc[b])))
+                if mirror:                  # slab boundary launches also fill the neighbour's ghost planes
+                    e("if (out_peer) st_global_v4(dst + {} + mirror, {});".format(b * domain.row_pitch, ", ".join(acc[b])))
+                e.close()
+            e("dst += {};".format(N1 * domain.row_pitch))
+            e.close()   # unit >= 4
+            e.close()   # unit >= 2
+            e("++unit;")
             e.close()
-        for b in range(BY):
-            e.open("if (store_ok{})".format(b))
-            e("st_global_v4(dst + {}, {});".format(b * domain.row_pitch, ", ".join(acc[b])))
-            if mirror:                  # slab boundary launches also fill the neighbour's ghost planes
-                e("if (out_peer) st_global_v4(dst + {} + mirror, {});".format(b * domain.row_pitch, ", ".join(acc[b])))
-            e.close()
-        e("dst += {};".format(N1 * domain.row_pitch))
-        e.close()   # unit >= 4
-        e.close()   # unit >= 2
-        e("++unit;")
+        if (P // S) % 2 == 1:
+            e("par ^= 1u;")
+        e.close()   # while
+
+    if step_kernel:
+        e.open("if (edge)")
+        emit_loop(True)
+        # every boundary CTA of this step has stored its planes (here and in the neighbour's ghost
+        # planes): the last one to arrive publishes the step number in the neighbours' memory
+        e('asm volatile("bar.sync 1, {};" ::: "memory");'.format(NCW * 32))
+        e.open("if (tid == 0)")
+        e("__threadfence_system();")
+        e("const u32 arrived = atomicAdd(sync + 2, 1u);")
+        e.open("if (arrived == gridDim.x * gridDim.y * {}u - 1u)".format(n_edge))
+        e("sync[2] = 0;                       // for the next step (which starts after this grid has completed)")
+        e("__threadfence_system();")
+        e("if (flag_up) st_release_sys(flag_up, step + 1u);")
+        e("if (flag_dn) st_release_sys(flag_dn, step + 1u);")
         e.close()
-    if (P // S) % 2 == 1:
-        e("par ^= 1u;")
-    e.close()   # while
+        e.close()
+        e.close()
+        e.open("else")
+        emit_loop(False)
+        e.close()
+    else:
+        emit_loop(mirror)
     e.close()   # kernel
     return e.text()
 
@@ -582,6 +705,9 @@ def make_plan(program, domain, device_props, options, second=None, second_domain
         # interior launches of a slab never mirror: a second entry point without that code
         # (the kernel is issue bound; the unused mirror stores cost about 6 %)
         source += generate(program, domain, cfg, function=FUNCTION + "_interior", mirror=False, prologue=False)
+        if second is None:
+            # one launch per exchange step: boundary planes first, then the interior (multi_gpu.py)
+            source += generate(program, domain, cfg, function=FUNCTION + "_step", prologue=False, step_kernel=True)
     n0, n1, n2 = program.shape
     row_pitch = domain.row_pitch
     specs = [TensorMapSpec(0, (n2, n1, n0), (row_pitch * 4, n1 * row_pitch * 4), (cfg.PITCH, cfg.ROWS, 1),
@@ -602,4 +728,14 @@ def make_plan(program, domain, device_props, options, second=None, second_domain
     plan = CudaPlan(program, domain, 'temporal', source, FUNCTION, options, geometry,
                     tensor_maps=specs, notes={'config': cfg.describe()})
     plan.function_no_peer = FUNCTION + "_interior" if domain.is_slab else None
+    plan.function_step = FUNCTION + "_step" if (domain.is_slab and second is None) else None
+
+    def step_geometry(a0_begin, a0_end):
+        """grid of the one-launch step: the interior chunks of [a0_begin, a0_end) preceded by one
+        z-slice per neighbouring slab (the boundary planes)"""
+        launch = geometry(a0_begin, a0_end)
+        edges = int(domain.open_lo) + int(domain.open_hi)
+        launch.grid = (launch.grid[0], launch.grid[1], launch.grid[2] + edges)
+        return launch
+    plan.step_geometry = step_geometry
     return plan

@@ -155,6 +155,7 @@ class SlabStencil(object):
         self.interior_done = self.device.new_event()
         self._events_armed = False
         self._ghosts_stale = False
+        self._step_blocks = {}
         self.peers = {}
         self.exchange = os.environ.get("STENCIL_CUDA_EXCHANGE", "peer") if slab.ghosted else "none"
         if self.exchange not in ("peer", "nccl", "none"):
@@ -281,9 +282,7 @@ class SlabStencil(object):
         self.runtime.launch(self.device.utils(), "sc_fill_uniform", geometry,
                             [ctypes.c_void_p(self._current().ptr), ctypes.c_uint64(count), ctypes.c_uint64(seed),
                              ctypes.c_uint64(offset % (1 << 64)), ctypes.c_float(scale)], self.device.stream)
-        self.device.synchronize()
-        if slab.ghosted:
-            self.dist.barrier()
+        self._resync_flags()
 
     def host_window(self):
         """Global axis-0 plane range [lo, hi) this rank needs from the host: its real planes plus
@@ -341,8 +340,21 @@ class SlabStencil(object):
                     ctypes.c_void_p(self.peers[neighbour]["buffers"][index] + destination[0] * plane_bytes),
                     ctypes.c_void_p(self.buffers[index].ptr + source[0] * plane_bytes),
                     (source[1] - source[0]) * plane_bytes, self.edge_stream))
-        self.quiesce()
+        self._resync_flags()
         self._ghosts_stale = False
+
+    def _resync_flags(self):
+        """Every rank is about to be quiescent with up-to-date ghost planes: set this rank's flag
+        words to the number of steps taken so far (sweeps that were no exchange steps -- apply_host
+        -- advanced the step count without anybody publishing it)."""
+        self.quiesce()
+        if self.slab.ghosted and self.exchange == "peer":
+            for offset in (0, 4):
+                self.runtime.check(self.library.sc_stream_write_value32(
+                    self.device.stream, ctypes.c_void_p(self.flags.ptr + offset), self.step))
+            self.runtime.check(self.library.sc_memset32_async(
+                ctypes.c_void_p(self.flags.ptr + 8), 0, 1, self.device.stream))
+            self.quiesce()
 
     def load(self, global_grid):
         """Copy this rank's planes (plus ghost planes) of a host array of the global shape."""
@@ -355,15 +367,13 @@ class SlabStencil(object):
         destination = self._current().ptr + local_lo * slab.plane_elems * 4
         self.runtime.check(self.library.sc_memcpy_h2d_async(
             ctypes.c_void_p(destination), ctypes.c_void_p(part.ctypes.data), part.nbytes, self.device.stream))
-        self.device.synchronize()
-        if slab.ghosted:
-            self.dist.barrier()
+        self._resync_flags()
         self._ghosts_stale = False
 
     def launches_per_step(self):
         """kernel launches one ``iterate`` step enqueues on this rank (a step = one sweep, or a
         fused pair of sweeps)"""
-        if not self.slab.ghosted:
+        if not self.slab.ghosted or self._step_kernel_available():
             return 1
         edges = int(self.slab.open_lo) + int(self.slab.open_hi)
         return 1 + edges + (1 if self.exchange == "peer" else 0)
@@ -446,6 +456,8 @@ class SlabStencil(object):
         signal_geometry = type("L", (), dict(grid=(1, 1, 1), block=(32, 1, 1), cluster=(1, 1, 1), smem=0))()
         exchanging = bool(up or down)
         remaining = sweeps
+        if exchanging and remaining >= 2 and self._step_kernel_available():
+            remaining -= 2 * self._enqueue_fused_steps(remaining // 2)
         while remaining > 0:
             fused = self.fused is not None and remaining >= 2
             applied = 2 if fused else 1
@@ -497,6 +509,69 @@ class SlabStencil(object):
             self.step += 1
             self.sweep += applied
             remaining -= applied
+
+    # -- one launch per exchange step ---------------------------------------------------------------
+    def _step_kernel_available(self):
+        return (self.fused is not None and self.exchange == "peer"
+                and getattr(self.fused[0], "function_step", None) is not None
+                and os.environ.get("STENCIL_CUDA_STEP_KERNEL", "1") not in ("0", ""))
+
+    def _enqueue_fused_steps(self, count):
+        """``count`` fused double sweeps, each ONE launch of ``stencil_temporal2_step``: its first CTAs
+        compute the boundary planes next to each neighbour (waiting for the neighbour's flag, storing
+        into the neighbour's ghost planes, publishing this rank's flag when all are done), the rest
+        the interior.  All launches are enqueued by one C call (``sc_launch_steps``) on the main
+        stream, with programmatic dependent launch; the GPUs synchronise among themselves through
+        the flag words, the host is not involved."""
+        runtime, library, slab = self.runtime, self.library, self.slab
+        plan, module = self.fused
+        programmatic = 0 if os.environ.get("STENCIL_CUDA_PDL", "1") in ("0", "") else 1
+        if programmatic:
+            module = self.concrete._dependent_launch_module(plan)
+        main = self.device.stream
+        if self._events_armed:                    # sweeps enqueued the two-stream way come first
+            runtime.check(library.sc_stream_wait_event(main, self.edge_done))
+        top, interior, bottom = slab.ranges()
+        geometry = plan.step_geometry(interior[0], interior[1])
+        up, down = self.peers.get(slab.rank - 1), self.peers.get(slab.rank + 1)
+        plane = slab.plane_elems
+        blocks = []
+        for parity in (self.step % 2, (self.step + 1) % 2):
+            current, target_index = self.buffers[parity].ptr, (parity + 1) % 2
+            key = ("step", parity)
+            block = self._step_blocks.get(key)
+            if block is None:
+                values = [ctypes.c_void_p(current)] + [ctypes.c_void_p(b.ptr) for b in self.table_buffers]
+                for spec in plan.tensor_maps:
+                    values.append(self.concrete._tensor_map(spec, current))
+                values += [ctypes.c_void_p(self.buffers[target_index].ptr),
+                           ctypes.c_int(interior[0]), ctypes.c_int(interior[1]), ctypes.c_int(geometry.extra[0]),
+                           ctypes.c_void_p(up["buffers"][target_index] if up else 0),
+                           ctypes.c_longlong(slab.counts[slab.rank - 1] * plane if up else 0),
+                           ctypes.c_void_p(down["buffers"][target_index] if down else 0),
+                           ctypes.c_longlong(-slab.planes * plane if down else 0),
+                           ctypes.c_int(top[0]), ctypes.c_int(top[1]), ctypes.c_int(bottom[0]), ctypes.c_int(bottom[1]),
+                           ctypes.c_void_p(self.flags.ptr),
+                           ctypes.c_void_p(up["flags"] + 4 if up else 0),        # I am the upper neighbour's lower one
+                           ctypes.c_void_p(down["flags"] if down else 0),
+                           ctypes.c_uint32(0)]
+                pointers = (ctypes.c_void_p * len(values))(
+                    *[ctypes.cast(ctypes.byref(v), ctypes.c_void_p) for v in values])
+                block = (values, pointers)
+                self._step_blocks[key] = block
+            blocks.append(block)
+        step_arg = len(blocks[0][0]) - 1
+        grid = (ctypes.c_uint32 * 3)(*geometry.grid)
+        threads = (ctypes.c_uint32 * 3)(*geometry.block)
+        runtime.check(library.sc_launch_steps(module.handle, plan.function_step.encode(), grid, threads,
+                                              geometry.smem, main, blocks[0][1], blocks[1][1], count,
+                                              programmatic, step_arg, self.step), "fused exchange steps")
+        runtime.check(library.sc_event_record(self.interior_done, main))
+        runtime.check(library.sc_event_record(self.edge_done, main))
+        self._events_armed = True
+        self.step += count
+        self.sweep += 2 * count
+        return count
 
     def join(self):
         """Make the main stream wait for the edge stream's last sweep (for timing with events

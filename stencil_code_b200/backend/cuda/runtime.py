@@ -69,6 +69,8 @@ SYMBOLS = {
                                 ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), _I]),
     "sc_launch": (_I, [_VP, ctypes.c_char_p, _U32x3, _U32x3, _U32x3, ctypes.c_uint32, _VP, _PVP]),
     "sc_launch_pingpong": (_I, [_VP, ctypes.c_char_p, _U32x3, _U32x3, ctypes.c_uint32, _VP, _PVP, _PVP, _I, ctypes.c_uint32]),
+    "sc_launch_steps": (_I, [_VP, ctypes.c_char_p, _U32x3, _U32x3, ctypes.c_uint32, _VP, _PVP, _PVP, _I, ctypes.c_uint32,
+                             _I, ctypes.c_uint32]),
     "sc_stream_create": (_I, [_PVP]),
     "sc_stream_destroy": (_I, [_VP]),
     "sc_stream_synchronize": (_I, [_VP]),

@@ -560,6 +560,43 @@ int sc_launch_pingpong(sc_module* module, const char* function, const uint32_t g
     return SC_OK;
 }
 
+int sc_launch_steps(sc_module* module, const char* function, const uint32_t grid[3],
+                    const uint32_t block[3], uint32_t dynamic_smem, void* stream,
+                    void** args_even, void** args_odd, int count, uint32_t flags,
+                    int step_arg, uint32_t first_step) {
+    if (!module || !function || !grid || !block || !args_even || !args_odd)
+        return fail(SC_EINVAL, "NULL argument");
+    if (step_arg < 0 || !args_even[step_arg] || !args_odd[step_arg])
+        return fail(SC_EINVAL, "step_arg does not name a parameter");
+    CUfunction fn;
+    int rc = get_function(module, function, &fn);
+    if (rc != SC_OK) return rc;
+    rc = optin_smem(module, function, fn, dynamic_smem);
+    if (rc != SC_OK) return rc;
+    CUlaunchConfig config;
+    memset(&config, 0, sizeof config);
+    config.gridDimX = grid[0]; config.gridDimY = grid[1]; config.gridDimZ = grid[2];
+    config.blockDimX = block[0]; config.blockDimY = block[1]; config.blockDimZ = block[2];
+    config.sharedMemBytes = dynamic_smem;
+    config.hStream = reinterpret_cast<CUstream>(stream);
+    CUlaunchAttribute attribute;
+    memset(&attribute, 0, sizeof attribute);
+    if (flags & SC_LAUNCH_PROGRAMMATIC) {
+        attribute.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+        attribute.value.programmaticStreamSerializationAllowed = 1;
+        config.attrs = &attribute;
+        config.numAttrs = 1;
+    }
+    for (int i = 0; i < count; ++i) {
+        void** args = (i & 1) ? args_odd : args_even;
+        *static_cast<uint32_t*>(args[step_arg]) = first_step + (uint32_t)i;   // copied by the launch
+        CUresult cu = g_drv.cuLaunchKernelEx_(&config, fn, args, nullptr);
+        if (cu != CUDA_SUCCESS)
+            return cuda_fail(cu, (std::string("cuLaunchKernelEx(") + function + ")").c_str());
+    }
+    return SC_OK;
+}
+
 // ---- streams and events ------------------------------------------------------------------------
 int sc_stream_create(void** stream) {
     if (!stream) return fail(SC_EINVAL, "stream is NULL");

@@ -90,6 +90,30 @@ def main():
             failures += not same
         dist.barrier()
 
+    # 1c. host -> ONE sweep -> host per rank (apply_host: the pipelined end-to-end path, ghost planes
+    #     from the host window), then four more sweeps on the device (ghost planes refreshed first)
+    shape = (96, 256, 512)
+    grid = numpy.random.RandomState(9).random_sample(shape).astype(numpy.float32)
+    slab = SlabStencil(Jacobi3D(1.0, 0.25), shape, device_index=local_rank)
+    lo, hi = slab.host_window()
+    first = numpy.array(slab.apply_host(numpy.ascontiguousarray(grid[lo:hi])))
+    slab.iterate(4)
+    parts_one, parts_five = [None] * world, [None] * world
+    dist.all_gather_object(parts_one, first)
+    dist.all_gather_object(parts_five, numpy.array(slab.result()))
+    slab.close()
+    if rank == 0:
+        python_side = Jacobi3D(1.0, 0.25, backend='python')
+        expected = reference_c(python_side, grid, variant='c_parallel')
+        same_one = (numpy.concatenate(parts_one, axis=0).view(numpy.uint32) == expected.view(numpy.uint32)).all()
+        for _ in range(4):
+            expected = reference_c(python_side, expected, variant='c_parallel')
+        same_five = (numpy.concatenate(parts_five, axis=0).view(numpy.uint32) == expected.view(numpy.uint32)).all()
+        print("apply_host check 96x256x512, {} ranks: one sweep {}, then iterate(4) {}".format(
+            world, "ok" if same_one else "MISMATCH", "ok" if same_five else "MISMATCH"))
+        failures += (not same_one) + (not same_five)
+    dist.barrier()
+
     # 2. larger grid (stream strategy, many chunks), k GPUs vs 1 GPU (plain single sweeps) by checksum
     shape = (256, 256, 512)
     slab = SlabStencil(Jacobi3D(1.0, 0.25), shape, device_index=local_rank)

@@ -1,21 +1,12 @@
-set -x
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "temporal or iterate or long_iterated or strict or extreme or out_tensor or apply_host" > gpurun_out/r2_t2.log 2>&1; tail -4 gpurun_out/r2_t2.log
-python -m pytest tests/test_fusion.py tests/test_gpu_fullsize.py -m gpu -x -q -k "jacobi or fus" > gpurun_out/r2_t3.log 2>&1; tail -4 gpurun_out/r2_t3.log
-python -m pytest tests/test_gpu_baseline_oracle.py -m gpu -x -q -k "c5" > gpurun_out/r2_t4.log 2>&1; tail -4 gpurun_out/r2_t4.log
-{
-python tools/probe_iter.py 2048x1024x1024 40
-STENCIL_CUDA_NO_FMA=1 python tools/probe_iter.py 2048x1024x1024 40
-STENCIL_CUDA_TEMPORAL_SHFL=0 python tools/probe_iter.py 2048x1024x1024 40
-STENCIL_CUDA_TEMPORAL_TILE="prefetch=2" python tools/probe_iter.py 2048x1024x1024 40
-STENCIL_CUDA_TEMPORAL_TILE="prefetch=1" python tools/probe_iter.py 2048x1024x1024 40
-STENCIL_CUDA_TEMPORAL_TILE="MY=32,BY=2,NCW=16,prefetch=1" python tools/probe_iter.py 2048x1024x1024 40
-STENCIL_CUDA_TEMPORAL_TILE="MY=32,BY=2,NCW=16,prefetch=4" python tools/probe_iter.py 2048x1024x1024 40
-STENCIL_CUDA_TEMPORAL_TILE="MY=32,BY=4,NCW=8,prefetch=1" python tools/probe_iter.py 2048x1024x1024 40
-STENCIL_CUDA_TEMPORAL_TILE="MY=32,BY=4,NCW=8,prefetch=4" python tools/probe_iter.py 2048x1024x1024 40
-STENCIL_CUDA_TEMPORAL_TILE="MY=64,BY=4,NCW=16,prefetch=1" python tools/probe_iter.py 2048x1024x1024 40
-STENCIL_CUDA_TEMPORAL=0 python tools/probe_iter.py 2048x1024x1024 40
-python tools/probe_iter.py 2048x1024x1024 40 copy
-python tools/probe_iter.py 256x1024x1024 40
-python tools/probe_iter.py 512x512x512 40
-} > gpurun_out/r2_probe1.log 2>&1
-cat gpurun_out/r2_probe1.log | cut -c1-150
+T="timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+$T --master-port 29511 tests/multi_gpu_check.py > gpurun_out/r2_mg_check.log 2>&1; grep -E "check|MULTI" gpurun_out/r2_mg_check.log | tail -20
+$T --master-port 29513 bench.py --gpus 2 --steps 100 --warmup 5 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; tail -c 300 gpurun_out/r2_bench_n2.err
+STENCIL_CUDA_STEP_KERNEL=0 $T --master-port 29514 bench.py --gpus 2 --steps 100 --warmup 5 --quick > gpurun_out/r2_bench_n2_old.json 2> gpurun_out/r2_bench_n2_old.err
+python - <<'PY'
+import json
+for f in ("gpurun_out/r2_bench_n2.json","gpurun_out/r2_bench_n2_old.json"):
+    try:
+        d=json.loads(open(f).read().strip().split("\n")[-1])
+        print(f, d["value"], d["ms_per_step"], d.get("parity"), d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["raw_copy_floor_ms"], d["e2e"]["job_100_sweeps"]["value"], (d.get("one_gpu_same_workload") or {}).get("value"))
+    except Exception as e: print(f, "ERR", e)
+PY
