@@ -264,20 +264,22 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
     e("const int y0 = blockIdx.y * {} - {};".format(cfg.OUT_ROWS, HY))
     n_edge = int(domain.open_lo) + int(domain.open_hi) if step_kernel else 0
     if step_kernel:
-        e("// z-slices: boundary planes first ({} neighbour{}), then the interior chunks".format(
+        e("// z-slices: the chunk(s) at the slab's open end(s) first ({} neighbour{}), then the middle chunks".format(
             n_edge, "" if n_edge == 1 else "s"))
-        e("int u_begin, u_end;")
+        e("int u_begin, u_end, mir_lo = 0, mir_hi = 0;      // [mir_lo, mir_hi): planes that also go to the neighbour")
         e("float* out_peer = nullptr; i64 peer_shift = 0; const u32* wait_flag = nullptr;")
         e("const bool edge = blockIdx.z < {};".format(n_edge))
         first = True
         if domain.open_lo:
             e.open("if (blockIdx.z == 0)")
             e("u_begin = top_begin; u_end = top_end; out_peer = peer_up; peer_shift = shift_up; wait_flag = sync;")
+            e("mir_lo = top_begin; mir_hi = top_begin + {};".format(domain.slab_ghost))
             e.close()
             first = False
         if domain.open_hi:
             e.open("{}if (blockIdx.z == {})".format("" if first else "else ", 0 if first else 1))
             e("u_begin = bot_begin; u_end = bot_end; out_peer = peer_dn; peer_shift = shift_dn; wait_flag = sync + 1;")
+            e("mir_lo = bot_end - {}; mir_hi = bot_end;".format(domain.slab_ghost))
             e.close()
             first = False
         e.open("{}".format("" if first else "else"))
@@ -647,11 +649,15 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                         value = mid_own(phase, 0, b, j) if copy else "0.0f"
                         e("if (zo_halo || ({} & {}u)) {} = {};".format(mask2, 1 << (b * 4 + j), acc[b][j], value))
                 e.close()
+            if mirror and step_kernel:
+                e("const int zs = p_first + unit - 2;")
+                e("const bool to_peer = zs >= mir_lo && zs < mir_hi;")
             for b in range(BY):
                 e.open("if (store_ok{})".format(b))
                 e("st_global_v4(dst + {}, {});".format(b * domain.row_pitch, ", ".join(acc[b])))
                 if mirror:                  # slab boundary launches also fill the neighbour's ghost planes
-                    e("if (out_peer) st_global_v4(dst + {} + mirror, {});".format(b * domain.row_pitch, ", ".join(acc[b])))
+                    e("if ({}) st_global_v4(dst + {} + mirror, {});".format(
+                        "to_peer" if step_kernel else "out_peer", b * domain.row_pitch, ", ".join(acc[b])))
                 e.close()
             e("dst += {};".format(N1 * domain.row_pitch))
             e.close()   # unit >= 4
@@ -731,11 +737,31 @@ def make_plan(program, domain, device_props, options, second=None, second_domain
     plan.function_step = FUNCTION + "_step" if (domain.is_slab and second is None) else None
 
     def step_geometry(a0_begin, a0_end):
-        """grid of the one-launch step: the interior chunks of [a0_begin, a0_end) preceded by one
-        z-slice per neighbouring slab (the boundary planes)"""
+        """grid and chunking of the one-launch step over the slab's real planes [a0_begin, a0_end):
+        ``launch.ranges`` = (top chunk, middle range, bottom chunk); the chunk at each open end is a
+        z-slice of its own, scheduled first (its first / last ghost-depth planes also go to the
+        neighbour), the middle range is cut into chunks of ``launch.extra[0]`` planes"""
         launch = geometry(a0_begin, a0_end)
         edges = int(domain.open_lo) + int(domain.open_hi)
-        launch.grid = (launch.grid[0], launch.grid[1], launch.grid[2] + edges)
+        planes = a0_end - a0_begin
+        chunk_len, chunks = launch.extra[0], launch.grid[2]
+        if chunks < edges:                        # a thin slab: one chunk per open end at least
+            chunks = edges
+            chunk_len = -(-planes // chunks)
+            launch.extra = (chunk_len,)
+        if planes < edges * domain.slab_ghost:
+            raise StencilException("slab thinner than the planes it exchanges")
+        top = (a0_begin, min(a0_begin + chunk_len, a0_end)) if domain.open_lo else (a0_begin, a0_begin)
+        last_begin = a0_begin + (-(-planes // chunk_len) - 1) * chunk_len
+        bottom = (max(last_begin, top[1]), a0_end) if domain.open_hi else (a0_end, a0_end)
+        if domain.open_hi and bottom[1] - bottom[0] < domain.slab_ghost:
+            # the last chunk is a short remainder: it must hold every plane the neighbour receives
+            bottom = (a0_end - domain.slab_ghost, a0_end)
+            top = (top[0], min(top[1], bottom[0]))
+        middle = (top[1], bottom[0])
+        middle_chunks = -(-(middle[1] - middle[0]) // chunk_len) if middle[1] > middle[0] else 0
+        launch.grid = (launch.grid[0], launch.grid[1], max(1, edges + middle_chunks))
+        launch.ranges = (top, middle, bottom)
         return launch
     plan.step_geometry = step_geometry
     return plan

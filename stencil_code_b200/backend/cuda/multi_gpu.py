@@ -531,8 +531,9 @@ class SlabStencil(object):
         main = self.device.stream
         if self._events_armed:                    # sweeps enqueued the two-stream way come first
             runtime.check(library.sc_stream_wait_event(main, self.edge_done))
-        top, interior, bottom = slab.ranges()
-        geometry = plan.step_geometry(interior[0], interior[1])
+        lo, hi = slab.first_real, slab.first_real + slab.planes
+        geometry = plan.step_geometry(lo, hi)
+        top, interior, bottom = geometry.ranges
         up, down = self.peers.get(slab.rank - 1), self.peers.get(slab.rank + 1)
         plane = slab.plane_elems
         blocks = []

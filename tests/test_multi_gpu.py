@@ -113,3 +113,33 @@ def test_slabs_on_two_gpus_match_single_gpu_and_oracle(exchange):
         capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, STENCIL_CUDA_EXCHANGE=exchange))
     assert done.returncode == 0 and "MULTI_GPU_CHECK PASSED" in done.stdout, \
         done.stdout[-3000:] + done.stderr[-3000:]
+
+
+def test_step_kernel_geometry_covers_the_slab():
+    """One launch per exchange step: the chunk at each open end of the slab is a z-slice of its
+    own (scheduled first, holding every plane the neighbour receives), the middle chunks follow;
+    together they tile the real planes exactly once -- thick and thin slabs, one or two neighbours."""
+    import numpy
+    from stencil_code_b200.backend.cuda import codegen_temporal, planner, runtime
+    from stencil_code_b200.library.jacobi_3d import Jacobi3D
+    from stencil_code_b200.stencil_kernel import StencilArgConfig
+    specializer = Jacobi3D(1.0, 0.25).specializer
+    ghost = 2
+    for planes, (n1, n2) in ((4, (256, 512)), (5, (256, 512)), (12, (256, 512)), (32, (256, 512)), (70, (256, 512)),
+                             (130, (1024, 1024)), (256, (1024, 1024))):
+        for faces in ((True, True), (False, True), (True, False)):
+            shape = (planes + 2 * ghost, n1, n2)
+            plan = specializer.transform((StencilArgConfig(shape[0], numpy.dtype('float32'), 3, shape),),
+                                         open_faces=faces, slab_ghost=ghost)
+            fused = codegen_temporal.make_plan(plan.program, plan.domain, planner.B200, plan.options)
+            assert fused.function_step == "stencil_temporal2_step"
+            launch = fused.step_geometry(ghost, ghost + planes)
+            top, middle, bottom = launch.ranges
+            assert top[0] == ghost and bottom[1] == ghost + planes and top[1] == middle[0] and middle[1] == bottom[0]
+            assert (top[1] - top[0] >= ghost) if faces[0] else top[1] == top[0]
+            assert (bottom[1] - bottom[0] >= ghost) if faces[1] else bottom[1] == bottom[0]
+            middle_chunks = -(-(middle[1] - middle[0]) // launch.extra[0]) if middle[1] > middle[0] else 0
+            assert launch.grid[2] == sum(faces) + middle_chunks
+    # the three entry points cross-compile for sm_100a (with the griddepcontrol instructions in)
+    module = runtime.compile_source(fused.source, "step_check.cu", list(fused.options) + ["-DSC_PDL"])
+    assert module.cubin()[:4] == b"\x7fELF"
