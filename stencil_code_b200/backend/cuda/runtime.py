@@ -719,7 +719,10 @@ class ConcreteCudaStencil(object):
             self._temporal = False
             setting = os.environ.get("STENCIL_CUDA_TEMPORAL", "1")
             if setting not in ("0", ""):
-                from . import codegen_temporal
+                if self.program.dim == 2:
+                    from . import codegen_temporal2d as codegen_temporal      # rows streamed, all in registers
+                else:
+                    from . import codegen_temporal
                 ok, _ = codegen_temporal.eligible(self.program, self.plan.domain)
                 if ok and self.plan.strategy == 'stream' and setting != "force":
                     ok = codegen_temporal.worthwhile(
@@ -804,7 +807,10 @@ class ConcreteCudaStencil(object):
         eligible, its tiles would not pay, or STENCIL_CUDA_TEMPORAL=0."""
         entry = self._pairs.get(id(other))
         if entry is None:
-            from . import codegen_temporal
+            if self.program.dim == 2:
+                from . import codegen_temporal2d as codegen_temporal
+            else:
+                from . import codegen_temporal
             found = None
             setting = os.environ.get("STENCIL_CUDA_TEMPORAL", "1")
             if setting not in ("0", "") and self.plan.strategy == 'stream' and other.plan.strategy == 'stream':

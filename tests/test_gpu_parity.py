@@ -424,3 +424,60 @@ def test_apply_host_on_one_gpu_matches_oracle():
         for _ in range(3):
             expected = oracle_output(python_side, expected, variant='c_parallel')
         assert_bit_identical(numpy.array(slab.result()), expected)
+
+
+ROW_FUSED_SHAPES = [(40, 256), (37, 388), (130, 1024), (19, 2052), (64, 4096)]
+
+
+@pytest.mark.parametrize("mode", ["clamp", "zero", "copy"])
+@pytest.mark.parametrize("name", ["jacobi2d", "simple", "odd_weights", "conv5", "diagnostic"])
+def test_rank2_temporal_blocking_equals_separate_sweeps(name, mode, monkeypatch):
+    """iterate() on rank-2 grids fuses pairs of sweeps in registers (codegen_temporal2d): the
+    result must be bit-identical to sweeping n times -- checked against the CPU oracle applied n
+    times, on widths with one and several CTAs per row, full and partial sub-tiles."""
+    from cases import CONV5, OddWeights
+    from stencil_code_b200.library.convolution import ConvolutionFilter
+    from stencil_code_b200.library.diagnostic_stencil import DiagnosticStencil
+    from stencil_code_b200.library.jacobi_stencil import Jacobi
+    from stencil_code_b200.library.simple import SimpleKernel
+    monkeypatch.setenv("STENCIL_CUDA_TEMPORAL", "force")      # small grids: not "worthwhile"
+    monkeypatch.setenv("STENCIL_CUDA_STRATEGY", "stream")
+    make = {"jacobi2d": lambda backend: Jacobi(backend=backend, boundary_handling=mode),
+            "simple": lambda backend: SimpleKernel(backend=backend, boundary_handling=mode),
+            "odd_weights": lambda backend: OddWeights(backend=backend, boundary_handling=mode),
+            "conv5": lambda backend: ConvolutionFilter(CONV5 / 64.0, backend=backend, boundary_handling=mode),
+            "diagnostic": lambda backend: DiagnosticStencil(backend=backend, boundary_handling=mode)}[name]
+    for shape in ROW_FUSED_SHAPES:
+        grid = (numpy.random.RandomState(29).random_sample(shape) * 0.01).astype(numpy.float32)
+        stencil, python_side = make('cuda'), make('python')
+        hidden = (stencil.coefficients,) if name == "conv5" else ()
+        concrete = stencil.specializer.specialize((grid,) + hidden)
+        fused = concrete.temporal()
+        assert fused is not None and fused[0].function == "stencil_temporal2_rows", "rank-2 fused kernel expected"
+        expected = grid
+        for sweeps in (1, 2, 3, 4, 5):
+            expected = oracle_output(python_side, expected)
+            if sweeps in (2, 3, 5):
+                assert_bit_identical(stencil.iterate(grid, sweeps), expected)
+
+
+def test_rank2_pairs_fuse_into_one_launch(monkeypatch):
+    """fuse(a, b) of two different rank-2 stencils: one launch, same bits as b(a(grid))."""
+    from cases import OddWeights
+    from stencil_code_b200 import fuse
+    from stencil_code_b200.library.jacobi_stencil import Jacobi
+    from stencil_code_b200.library.simple import SimpleKernel
+    monkeypatch.setenv("STENCIL_CUDA_TEMPORAL", "force")
+    monkeypatch.setenv("STENCIL_CUDA_STRATEGY", "stream")
+    grid = (numpy.random.RandomState(31).random_sample((70, 1028)) * 0.01).astype(numpy.float32)
+    for mode in ("clamp", "zero", "copy"):
+        first, second = SimpleKernel(boundary_handling=mode), OddWeights(boundary_handling=mode)
+        pipeline = fuse(first, second)
+        result = pipeline(grid)
+        assert pipeline.last_schedule == ['pair']
+        expected = oracle_output(OddWeights(backend='python', boundary_handling=mode),
+                                 oracle_output(SimpleKernel(backend='python', boundary_handling=mode), grid))
+        assert_bit_identical(result, expected)
+        three = fuse(first, second, Jacobi(boundary_handling=mode))
+        expected = oracle_output(Jacobi(backend='python', boundary_handling=mode), expected)
+        assert_bit_identical(three(grid), expected)

@@ -1,11 +1,14 @@
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29516 tests/multi_gpu_check.py > gpurun_out/r2_mg_check8.log 2>&1; grep -E "MISMATCH|MULTI" gpurun_out/r2_mg_check8.log
-T="timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-$T --master-port 29513 bench.py --gpus 8 --steps 100 --warmup 5 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err; tail -c 300 gpurun_out/r2_bench_n8.err
-python - <<'PY'
-import json
-for f in ("gpurun_out/r2_bench_n8.json",):
-    try:
-        d=json.loads(open(f).read().strip().split("\n")[-1])
-        print(f, d["value"], d["ms_per_step"], d.get("parity"), d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["raw_copy_floor_ms"], d["e2e"]["job_100_sweeps"]["value"], (d.get("one_gpu_same_workload") or {}).get("value"))
-    except Exception as e: print(f, "ERR", e)
-PY
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "rank2" > gpurun_out/r2_t5.log 2>&1; tail -n 15 gpurun_out/r2_t5.log
+{
+for k in jacobi2d simple conv5; do
+timeout 120 python tools/probe_iter2d.py $k 16384x16384 40
+STENCIL_CUDA_TEMPORAL=0 timeout 120 python tools/probe_iter2d.py $k 16384x16384 40
+done
+timeout 120 python tools/probe_iter2d.py jacobi2d 16384x16384 40 zero
+timeout 120 python tools/probe_iter2d.py jacobi2d 8192x8192 40
+STENCIL_CUDA_TEMPORAL_TILE="NCW=4,BY=1" timeout 120 python tools/probe_iter2d.py jacobi2d 16384x16384 40
+STENCIL_CUDA_TEMPORAL_TILE="NCW=8,BY=1" timeout 120 python tools/probe_iter2d.py jacobi2d 16384x16384 40
+STENCIL_CUDA_TEMPORAL_TILE="NCW=4,BY=2,U=6,S=2" timeout 120 python tools/probe_iter2d.py jacobi2d 16384x16384 40
+STENCIL_CUDA_TEMPORAL_TILE="NCW=4,BY=2,U=6,S=4" timeout 120 python tools/probe_iter2d.py jacobi2d 16384x16384 40
+} 2>&1 | grep -E "GStencil|Error|error" | cut -c1-200 > gpurun_out/r2_probe3.log
+cat gpurun_out/r2_probe3.log
