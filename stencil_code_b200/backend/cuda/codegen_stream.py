@@ -78,6 +78,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* tm, u64*
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         :: "r"(sc_smem(dst)), "l"(tm), "r"(sc_smem(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ float lds_f32(u32 address) {       // read-only tables: not volatile, may be scheduled freely
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(address));
+    return v;
+}
 __device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d) {
     asm volatile("st.global@STOP@.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -596,6 +601,8 @@ def generate(program, domain, cfg):
             if param is not None and param[0] == 'table':
                 e("for (int k = tid; k < {n}; k += {t}) spar{s}[k] = a{a}[ipar{s}[k]];".format(
                     n=len(param[3]), t=cfg.threads, s=slot, a=param[2]))
+    for index, arg in sorted(replicated.items()):
+        e("const u32 repk{i} = sc_smem(rep{i}) + (u32)lane * 4u - 0x80000000u;".format(i=index))
     e("__syncthreads();")
     e("pdl_wait();                         // the grids may still be written by the preceding sweep")
     e()
@@ -850,9 +857,13 @@ def generate(program, domain, cfg):
         if fast is not None and (ref.arg in replicated or ref.arg in smem_tables):
             # the enclosing emitter prints the float operand; see _fast_floor_index
             operand = pp.expr_to_c(fast, current_tap_text[0], table_text, out_text=current_acc[0])
-            bits = "(__float_as_int(__fadd_rz(fabsf({}), 8388608.0f)) - 0x4B000000)".format(operand)
             if ref.arg in replicated:
-                return "rep{}[({} << 5) + lane]".format(ref.arg, bits)
+                # one shift-add forms the shared-memory address: the float's bits are 0x4B000000 + k,
+                # entry k of this lane lives 128 k bytes above repk (which has -(0x4B000000 << 7),
+                # i.e. 0x80000000 modulo 2^32, and the lane's word folded in)
+                return "lds_f32(repk{} + (__float_as_uint(__fadd_rz(fabsf({}), 8388608.0f)) << 7))".format(
+                    ref.arg, operand)
+            bits = "(__float_as_int(__fadd_rz(fabsf({}), 8388608.0f)) - 0x4B000000)".format(operand)
             return "tab{}[{}]".format(ref.arg, bits)
         if ref.arg in replicated:
             return "rep{}[(({}) << 5) + lane]".format(ref.arg, index_text)

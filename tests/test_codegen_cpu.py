@@ -146,7 +146,7 @@ def test_bilateral_is_tiled_rolled_and_uses_the_fast_table_index():
     source = plan.source
     assert "#pragma unroll 1" in source and "for (int tr_ = 0; tr_ < 19; ++tr_)" in source
     assert "__fadd_rz(fabsf(" in source and "8388608.0f" in source      # abs((int)x) as FADD.RZ
-    assert "rep2[" in source and "<< 5) + lane]" in source               # bank-replicated LUT
+    assert "rep2[" in source and "lds_f32(repk2 + (" in source and "<< 7))" in source   # bank-replicated LUT, one shift-add per gather
     assert len(source) < 80 * 1024                                       # 361 taps are NOT unrolled
     assert runtime.compile_source(source, "bilateral.cu", plan.options).cubin()[:4] == b"\x7fELF"
 
