@@ -513,6 +513,7 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                     ztests.append("zm >= {}".format(i_hi[0]))
                 e("const bool zm_halo = {};".format(" || ".join(ztests) if ztests else "false"))
                 e.open("if (zm_halo || halo_mask)")
+                e('asm volatile("" ::: "memory");     // keeps this rare case a branch, not selects for everyone')
                 for b in range(BY):
                     for j in range(4):
                         value = in_name(phase, 0, b, j) if copy else "0.0f"
@@ -643,6 +644,7 @@ def generate(program, domain, cfg, function=FUNCTION, mirror=None, prologue=True
                     ztests.append("zo >= {}".format(j_hi[0]))
                 e("const bool zo_halo = {};".format(" || ".join(ztests) if ztests else "false"))
                 e.open("if (zo_halo || {})".format(mask2))
+                e('asm volatile("" ::: "memory");     // keeps this rare case a branch, not selects for everyone')
                 for b in range(BY):
                     for j in range(4):
                         # 'copy': the halo of sweep 2 copies the halo of mid, which copied the input

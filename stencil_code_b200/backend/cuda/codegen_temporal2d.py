@@ -38,6 +38,7 @@ from .codegen_stream import PTX_HELPERS, TensorMapSpec, _Emitter, _group_loads, 
     _const_index
 
 FUNCTION = "stencil_temporal2_rows"
+SINGLE_FUNCTION = "stencil_rows"
 
 
 def eligible(program, domain):
@@ -91,21 +92,35 @@ def _extents(program, second=None):
     return (lo1[0], hi1[0]), (lo2[0], hi2[0]), hx
 
 
-def choose_config(program, device_props, second=None):
+def choose_config(program, device_props, second=None, depth=2):
+    """``depth`` 2: the fused two-sweep kernel; 1: the same row pipeline with a single sweep (the
+    single-sweep rank-2 kernel with compile-time ring indices, ``SINGLE_FUNCTION``)."""
     (lo1, hi1), (lo2, hi2), hx = _extents(program, second)
+    if depth == 1:
+        lo2 = hi2 = 0
     W1, W2 = hi1 - lo1 + 1, hi2 - lo2 + 1
     PADX = 4 if hx else 0
     override = {}
-    for item in filter(None, os.environ.get("STENCIL_CUDA_TEMPORAL_TILE", "").split(",")):
+    knob = "STENCIL_CUDA_TEMPORAL_TILE" if depth == 2 else "STENCIL_CUDA_ROWS_TILE"
+    for item in filter(None, os.environ.get(knob, "").split(",")):
         key, _, value = item.partition("=")
         override[key.strip()] = int(value)
     window = W1 * W2 // math.gcd(W1, W2)
     width = 4 + 2 * hx
     # registers: both windows, two accumulator quads, addresses
     best = None
-    for NCW, BY in ((4, 2), (4, 1), (8, 1), (2, 1)):
+    # measured on B200, 16384^2 (GStencil/s).  Fused, 4-point Jacobi: (4,2) 1491, (8,1) 1477, (4,1) 1373.
+    # Single sweeps, 5x5 convolution, clamp / zero / copy alike: (16,1) 772-776, (8,1) 641-753, (4,1) 677-697,
+    # (4,2) 648-685 (codegen_stream's kernel: 703-710); 4-point Jacobi: (8,1) 765, (16,1) 741 (codegen_stream: 772)
+    if depth == 2:
+        order = ((4, 2), (4, 1), (8, 1), (2, 1))
+    elif W1 >= 4:
+        order = ((16, 1), (8, 1), (4, 1), (2, 1))
+    else:
+        order = ((8, 1), (4, 1), (4, 2), (2, 1))
+    for NCW, BY in order:
         NCW, BY = override.get("NCW", NCW), override.get("BY", BY)
-        registers = 32 + BY * (W1 + W2) * width + BY * 8
+        registers = 32 + BY * (W1 + (W2 if depth == 2 else 0)) * width + BY * 8
         if registers > 168 and not override:
             continue
         # rows per stage: the window length where that keeps the phase count small
@@ -128,8 +143,8 @@ def choose_config(program, device_props, second=None):
         if program.uses_double() or (second is not None and second.uses_double()):
             blocks = min(blocks, 2)                 # double temporaries: leave room, avoid spills
         blocks = override.get("blocks", blocks)
-        out_cols = 128 - (8 if hx else 0)
-        best = Temporal2dConfig(NCW=NCW, BY=BY, U=U, S=S, HX=hx, PADX=PADX, PITCH=pitch, NSUB=n_sub, W1=W1, W2=W2, P=P,
+        out_cols = 128 - (8 if hx and depth == 2 else 0)
+        best = Temporal2dConfig(DEPTH=depth, NCW=NCW, BY=BY, U=U, S=S, HX=hx, PADX=PADX, PITCH=pitch, NSUB=n_sub, W1=W1, W2=W2, P=P,
                                 LO1=lo1, HI1=hi1, LO2=lo2, HI2=hi2, STAGE_FLOATS=stage_floats,
                                 STAGE_BYTES=n_sub * U * pitch * 4, SUB_FLOATS=sub_floats, OUT_COLS=out_cols,
                                 TX=n_sub * out_cols, smem_bytes=smem, threads=threads, blocks_per_sm=max(1, blocks))
@@ -171,7 +186,8 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
     i_lo, i_hi = domain.interior_lo, domain.interior_hi
     j_lo, j_hi = second_domain.interior_lo, second_domain.interior_hi
     two_masks = (tuple(i_lo), tuple(i_hi)) != (tuple(j_lo), tuple(j_hi))
-    LANE_PAD = 4 if HX else 0                      # the first / last lane of a sub-tile only produce halo
+    one_sweep = cfg.DEPTH == 1                     # the row enters the window, the result is stored
+    LANE_PAD = 4 if (HX and not one_sweep) else 0     # the first / last lane of a sub-tile only produce halo
     cols = list(range(-HX, 4 + HX))                # columns of a window row, relative to the quad
     _, const_refs, _, _ = table_plan(program, False)
     _, const_refs2, _, _ = table_plan(second, False)
@@ -251,7 +267,7 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
             b=b, by=BY, oc=OUTC, pad=LANE_PAD))
         e("const float* const src{b} = ring + (warp * {by} + {b}) * {sub} + {px} + lane * 4;".format(
             b=b, by=BY, sub=SUBF, px=PADX))
-        lane_ok = "lane >= 1 && lane <= 30 && " if HX else ""
+        lane_ok = "lane >= 1 && lane <= 30 && " if LANE_PAD else ""
         e("const bool store_ok{b} = {l}gx{b} >= 0 && gx{b} < {n};".format(b=b, l=lane_ok, n=N1))
         e("float* dst{b} = out + (i64)u_begin * {p} + gx{b};".format(b=b, p=pitch))
         if clamp and HX:
@@ -271,7 +287,10 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
     for (arg, index), ctype in sorted(const_refs.items()):
         e("const {} tc{}_{} = a{}[{}];".format(ctype, arg, index, arg, index))
     names = [in_name(slot, b, c) for slot in range(W1) for b in range(BY) for c in cols]
-    names += [mid_name(slot, b, c) for slot in range(W2) for b in range(BY) for c in cols]
+    if one_sweep:
+        names += [mid_name(0, b, j) for b in range(BY) for j in range(4)]          # the accumulators
+    else:
+        names += [mid_name(slot, b, c) for slot in range(W2) for b in range(BY) for c in cols]
     for first in range(0, len(names), 8):
         e("float {};".format(", ".join(n + " = 0.0f" for n in names[first:first + 8])))
     counter = [0]
@@ -357,70 +376,77 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
                 tests.append("rm >= {}".format(i_hi[0]))
             e("const bool rm_halo = {};".format(" || ".join(tests) if tests else "false"))
             e.open("if (rm_halo || halo_mask)")
+            e('asm volatile("" ::: "memory");     // keeps this rare case a branch, not selects for everyone')
             for b in range(BY):
                 for j in range(4):
                     value = in_name((s1 - HI1) % W1, b, j) if copy else "0.0f"
                     e("if (rm_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), mid_name(s2, b, j), value))
             e.close()
-        # the columns next to the quad come from the neighbouring lanes, once per mid row
-        for b in range(BY):
-            for c in cols:
-                if c < 0 or c > 3:
-                    e("{} = __shfl_{}_sync(0xffffffffu, {}, 1);".format(
-                        mid_name(s2, b, c), "up" if c < 0 else "down", mid_name(s2, b, c % 4)))
-        if clamp and HX:
+        if one_sweep:
             for b in range(BY):
-                e.open("if (x_edge{})".format(b))
-                column_fix(b, {c: mid_name(s2, b, c) for c in cols})
-                e.close()
-        if clamp and W2 > 1:
-            e.open("if (rm <= {} || rm > {})".format(c_lo[0], c_hi[0]))
-            e('asm volatile("" ::: "memory");')
-            prev = (s2 - 1) % W2
-            e.open("if (rm > {})".format(c_hi[0]))
+                e("if (store_ok{b}) st_global_v4(dst{b}, {v});".format(b=b, v=", ".join(mid_name(s2, b, j) for j in range(4))))
+                e("dst{b} += {p};".format(b=b, p=pitch))
+        else:
+            # the columns next to the quad come from the neighbouring lanes, once per mid row
             for b in range(BY):
-                e(" ".join("{} = {};".format(mid_name(s2, b, c), mid_name(prev, b, c)) for c in cols))
-            e.close()
-            e.open("else if (rm == {})".format(c_lo[0]))
-            for older in range(1, W2):
+                for c in cols:
+                    if c < 0 or c > 3:
+                        e("{} = __shfl_{}_sync(0xffffffffu, {}, 1);".format(
+                            mid_name(s2, b, c), "up" if c < 0 else "down", mid_name(s2, b, c % 4)))
+            if clamp and HX:
                 for b in range(BY):
-                    e(" ".join("{} = {};".format(mid_name((s2 - older) % W2, b, c), mid_name(s2, b, c)) for c in cols))
-            e.close()
-            e.close()
+                    e.open("if (x_edge{})".format(b))
+                    column_fix(b, {c: mid_name(s2, b, c) for c in cols})
+                    e.close()
+            if clamp and W2 > 1:
+                e.open("if (rm <= {} || rm > {})".format(c_lo[0], c_hi[0]))
+                e('asm volatile("" ::: "memory");')
+                prev = (s2 - 1) % W2
+                e.open("if (rm > {})".format(c_hi[0]))
+                for b in range(BY):
+                    e(" ".join("{} = {};".format(mid_name(s2, b, c), mid_name(prev, b, c)) for c in cols))
+                e.close()
+                e.open("else if (rm == {})".format(c_lo[0]))
+                for older in range(1, W2):
+                    for b in range(BY):
+                        e(" ".join("{} = {};".format(mid_name((s2 - older) % W2, b, c), mid_name(s2, b, c)) for c in cols))
+                e.close()
+                e.close()
 
-        # ---------------- sweep 2: output row zo = rm - HI2
-        e.open("if (unit >= {})".format((W1 - 1) + (W2 - 1)))
-        acc = [["acc{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
-        for b in range(BY):
-            e("float {};".format(", ".join(n + " = 0.0f" for n in acc[b])))
-        for statement in second.statements:
+            # ---------------- sweep 2: output row zo = rm - HI2
+            e.open("if (unit >= {})".format((W1 - 1) + (W2 - 1)))
+            acc = [["acc{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
             for b in range(BY):
-                for j in range(4):
-                    def tap_text(tap, b=b, j=j):
-                        dr, dc = tap.offset
-                        return mid_name((s2 + dr - HI2) % W2, b, j + dc)
-                    single = pp.PointProgram(2, second.shape, second.out_ctype, second.args, [statement],
-                                             second.ghost_depth, boundary)
-                    e(emit_statements(single, tap_text, table_text, acc=acc[b][j], indent="")[0])
-        if not clamp:
-            e("const int zo = rm - ({});".format(HI2))
-            mask2 = "halo_mask2" if two_masks else "halo_mask"
-            tests = []
-            if j_lo[0] > 0:
-                tests.append("zo < {}".format(j_lo[0]))
-            if j_hi[0] < N0:
-                tests.append("zo >= {}".format(j_hi[0]))
-            e("const bool zo_halo = {};".format(" || ".join(tests) if tests else "false"))
-            e.open("if (zo_halo || {})".format(mask2))
+                e("float {};".format(", ".join(n + " = 0.0f" for n in acc[b])))
+            for statement in second.statements:
+                for b in range(BY):
+                    for j in range(4):
+                        def tap_text(tap, b=b, j=j):
+                            dr, dc = tap.offset
+                            return mid_name((s2 + dr - HI2) % W2, b, j + dc)
+                        single = pp.PointProgram(2, second.shape, second.out_ctype, second.args, [statement],
+                                                 second.ghost_depth, boundary)
+                        e(emit_statements(single, tap_text, table_text, acc=acc[b][j], indent="")[0])
+            if not clamp:
+                e("const int zo = rm - ({});".format(HI2))
+                mask2 = "halo_mask2" if two_masks else "halo_mask"
+                tests = []
+                if j_lo[0] > 0:
+                    tests.append("zo < {}".format(j_lo[0]))
+                if j_hi[0] < N0:
+                    tests.append("zo >= {}".format(j_hi[0]))
+                e("const bool zo_halo = {};".format(" || ".join(tests) if tests else "false"))
+                e.open("if (zo_halo || {})".format(mask2))
+                e('asm volatile("" ::: "memory");     // keeps this rare case a branch, not selects for everyone')
+                for b in range(BY):
+                    for j in range(4):
+                        value = mid_name((s2 - HI2) % W2, b, j) if copy else "0.0f"
+                        e("if (zo_halo || ({} & {}u)) {} = {};".format(mask2, 1 << (b * 4 + j), acc[b][j], value))
+                e.close()
             for b in range(BY):
-                for j in range(4):
-                    value = mid_name((s2 - HI2) % W2, b, j) if copy else "0.0f"
-                    e("if (zo_halo || ({} & {}u)) {} = {};".format(mask2, 1 << (b * 4 + j), acc[b][j], value))
-            e.close()
-        for b in range(BY):
-            e("if (store_ok{b}) st_global_v4(dst{b}, {v});".format(b=b, v=", ".join(acc[b])))
-            e("dst{b} += {p};".format(b=b, p=pitch))
-        e.close()   # sweep 2
+                e("if (store_ok{b}) st_global_v4(dst{b}, {v});".format(b=b, v=", ".join(acc[b])))
+                e("dst{b} += {p};".format(b=b, p=pitch))
+            e.close()   # sweep 2
         e.close()   # sweep 1
         e("++unit;")
         e.close()
@@ -462,3 +488,45 @@ def make_plan(program, domain, device_props, options, second=None, second_domain
     plan.function_no_peer = None
     plan.function_step = None
     return plan
+
+
+# ---- the same row pipeline with ONE sweep: the single-sweep kernel of rank-2 grids -------------------
+def single_applicable(program, domain):
+    """Single sweeps of rank-2 stencils take this generator (``stencil_rows``) where it applies --
+    compile-time ring indices and register-side axis-0 clamp instead of the per-row index arithmetic
+    that bounds ``codegen_stream``'s rank-2 kernel -- and ``codegen_stream`` otherwise (several grid
+    arguments, data-indexed tables, slabs, padded rows, wide reach, large windows)."""
+    if os.environ.get("STENCIL_CUDA_ROWS", "1") in ("0", ""):
+        return False
+    ok, _ = eligible(program, domain)
+    if not ok:
+        return False
+    lo, hi = program.tap_extent()
+    width = 4 + 2 * max(-lo[1], hi[1])
+    return 32 + (hi[0] - lo[0] + 1) * width + 8 <= 168
+
+
+def make_single_plan(program, domain, device_props, options):
+    from .transformer import CudaPlan
+    from .planner import Launch
+    from .codegen_stream import plan_chunks_adaptive
+    cfg = choose_config(program, device_props, depth=1)
+    source = generate(program, domain, cfg, function=SINGLE_FUNCTION)
+    n0, n1 = program.shape
+    specs = [TensorMapSpec(0, (n1, n0), (domain.row_pitch * 4,), (cfg.PITCH, cfg.U), tag="rows")]
+    tiles = -(-n1 // cfg.TX)
+    slots = device_props.sm_count * cfg.blocks_per_sm
+    floors = (max(4 * cfg.U, 64), 2 * cfg.U)
+
+    def geometry(a0_begin, a0_end):
+        n_units = a0_end - a0_begin
+        chunks = plan_chunks_adaptive(n_units, tiles, slots, cfg.W1, floors, device_props.sm_count)
+        chunk_len = -(-n_units // chunks)
+        chunks = -(-n_units // chunk_len)
+        launch = Launch((tiles, 1, chunks), (cfg.threads, 1, 1), cfg.smem_bytes)
+        launch.extra = (chunk_len,)
+        return launch
+
+    notes = dict(cfg.describe(), rank=2, strategy="rows", mode="regwin", embedded_plane=False, static_smem=0)
+    return CudaPlan(program, domain, 'stream', source, SINGLE_FUNCTION, options, geometry,
+                    tensor_maps=specs, notes={'config': notes})

@@ -53,6 +53,10 @@ def plan(program, domain, device_props=None, forced_strategy=None, options=()):
         ok, why = codegen_stream.applicable(program, domain, device_props, forced=True)
         if not ok:
             raise StencilException("strategy 'stream' cannot handle this stencil: " + why)
+        if program.dim == 2 and not codegen_stream.wants_plane_embedding(program, domain):
+            from . import codegen_temporal2d
+            if codegen_temporal2d.single_applicable(program, domain):
+                return codegen_temporal2d.make_single_plan(program, domain, device_props, options)
         return codegen_stream.make_plan(program, domain, device_props, options)
     if strategy != 'direct':
         raise StencilException("unknown strategy '{}'".format(strategy))
