@@ -134,8 +134,32 @@ def cases(sk):
     ]
 
 
+def mallard(sk):
+    """The reference's real-image fixture: ``demo/mallard.raw`` (800x800 8-bit grey) through the
+    unmodified reference ``BetterBilateralFilter()`` -- the filter of ``demo/bilateral_filter.py:19``
+    with its default sigmas 3 / 70 (radius 9) -- on its python backend.  A 64x64 crop keeps the
+    fixture small (the pure-python backend needs ~10 s for it); the grid is filled as the demo
+    does, ``in_grid[(x, y)] = pixels[y * width + x]`` (``demo/bilateral_filter.py:22-24``)."""
+    from stencil_code.library.better_bilateral_filter import BetterBilateralFilter
+    width = height = 800
+    with open(os.path.join(REFERENCE, "demo", "mallard.raw"), "rb") as handle:
+        pixels = numpy.frombuffer(handle.read(width * height), numpy.uint8)
+    image = pixels.reshape(height, width).T.astype(numpy.float32)       # [x, y], as the demo indexes it
+    x0, y0, n = 368, 300, 64                                           # a textured part of the bird
+    crop = numpy.ascontiguousarray(image[x0:x0 + n, y0:y0 + n])
+    out = BetterBilateralFilter(backend='python')(crop)
+    assert out.dtype == numpy.float32 and out.shape == crop.shape
+    path = os.path.join(HERE, "mallard_crop__clamp.npz")
+    numpy.savez_compressed(path, image_in=crop, image_out=out, origin=numpy.array([x0, y0]),
+                           mean_in=numpy.array(float(pixels.astype(numpy.float64).mean())))
+    print("wrote", os.path.basename(path), crop.shape, "grey levels", int(crop.min()), "..", int(crop.max()))
+
+
 def main():
     sk = import_reference()
+    if "--mallard-only" in sys.argv:
+        mallard(sk)
+        return
     written = 0
     for name, factory, extra, shape, scale, modes in cases(sk):
         for mode in modes:
@@ -157,6 +181,7 @@ def main():
             written += 1
             print("wrote", os.path.basename(path), shape, mode)
     print(written, "fixtures")
+    mallard(sk)
 
 
 if __name__ == "__main__":

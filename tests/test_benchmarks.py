@@ -51,3 +51,27 @@ def test_demo_on_cuda_matches_oracle():
     expected = oracle_output(BetterBilateralFilter(3, 70, backend='python'), image.astype(numpy.float32))
     from demo.bilateral_filter import rescale_to_intensity
     numpy.testing.assert_array_equal(result, rescale_to_intensity(expected, float(image.mean())))
+
+
+@pytest.mark.gpu
+def test_demo_on_the_reference_image_crop():
+    """``demo/mallard.raw`` (64x64 crop committed as a golden vector together with the unmodified
+    reference's output): backend='cuda' equals the oracle bit for bit, the reference's python
+    backend on the interior to 6 decimals, and the demo's normalised 8-bit image
+    (``demo/bilateral_filter.py:32-34``) to one grey level."""
+    import os
+    from cases import oracle_output
+    from demo.bilateral_filter import rescale_to_intensity
+    from stencil_code_b200.library.better_bilateral_filter import BetterBilateralFilter
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mallard_crop__clamp.npz")
+    data = numpy.load(golden)
+    image = data["image_in"]
+    filtered = numpy.asarray(BetterBilateralFilter(backend='cuda')(image))
+    expected = oracle_output(BetterBilateralFilter(backend='python'), image)
+    assert (filtered.view(numpy.uint32) == expected.view(numpy.uint32)).all()
+    interior = BetterBilateralFilter(backend='python').interior_points_slice()
+    scale = float(numpy.abs(data["image_out"]).max())
+    numpy.testing.assert_array_almost_equal(filtered[interior] / scale, data["image_out"][interior] / scale, decimal=6)
+    ours = rescale_to_intensity(filtered[interior], float(image[interior].mean())).astype(numpy.int64)
+    theirs = rescale_to_intensity(data["image_out"][interior], float(image[interior].mean())).astype(numpy.int64)
+    assert numpy.abs(ours - theirs).max() <= 1
