@@ -21,6 +21,7 @@ BLOCK_THREADS = 256
 def generate(program, domain, config=None):
     if config is not None and config.get('kind') == 'tiled':
         return generate_tiled(program, domain, config)
+    vector = config['V'] if config is not None and config.get('kind') == 'vector1d' else 0
     dim = program.dim
     shape = program.shape
     big = program.npoints >= 2 ** 31 - 2 ** 20
@@ -79,17 +80,53 @@ def generate(program, domain, config=None):
     lines.append("    pdl_launch_dependents();")
     lines.append("    pdl_wait();")
     lines.append("    const i64 t = (i64)blockIdx.x * {} + threadIdx.x;".format(BLOCK_THREADS))
-    lines.append("    if (t >= (i64)(a0_end - a0_begin) * {}LL) return;".format(per0))
-    if dim == 1:
-        lines.append("    const int i0 = a0_begin + (int)t;")
+    leave = "return"
+    if vector:
+        # rank 1, large grids: a thread owns V consecutive points (16 bytes).  Groups that lie V points
+        # inside the grid take three 128-bit loads and one 128-bit store (no index clamping can bind,
+        # no halo point is among them); the groups at either end, ranges that do not start on a
+        # 16-byte boundary and the tail run the one-point code below, point by point.
+        T, V, n = program.out_ctype, vector, shape[0]
+        vec_t = "float4" if V == 4 else "double2"
+        lines.append("    const i64 first = (i64)a0_begin + t * {};".format(V))
+        lines.append("    if (first >= a0_end) return;")
+        lines.append("    const int base = (int)first;")
+        lines.append("    const bool aligned = ((((unsigned long long)a0) | ((unsigned long long)out)) & 15ull) == 0 "
+                     "&& (a0_begin % {}) == 0;     // (a view into a larger tensor may start anywhere)".format(V))
+        lines.append("    if (aligned && base >= {v} && base + {w} <= {n} && base + {v} <= a0_end) {{".format(
+            v=V, w=2 * V, n=n))
+        for name, where in (("qm", "base - {}".format(V)), ("q0", "base"), ("qp", "base + {}".format(V))):
+            lines.append("        const {vt} {nm} = *reinterpret_cast<const {vt}*>(a0 + {w});".format(vt=vec_t, nm=name, w=where))
+        values = {}
+        for k, name in enumerate(("qm", "q0", "qp")):
+            for c in range(V):
+                values[(k - 1) * V + c] = "{}.{}".format(name, "xyzw"[c])
+        for j in range(V):
+            lines.append("        {} acc{} = {};".format(T, j, ctype_zero(T)))
+            body = emit_statements(program, lambda tap, j=j: values[j + tap.offset[0]], table_text,
+                                   acc="acc{}".format(j), indent="        ")
+            lines.extend(body)
+        make = "make_float4" if V == 4 else "make_double2"
+        lines.append("        *reinterpret_cast<{vt}*>(out + base) = {mk}({a});".format(
+            vt=vec_t, mk=make, a=", ".join("acc{}".format(j) for j in range(V))))
+        lines.append("        return;")
+        lines.append("    }")
+        lines.append("    for (int k = 0; k < {}; ++k) {{".format(V))
+        lines.append("    const int i0 = base + k;")
+        lines.append("    if (i0 >= a0_end) break;")
+        leave = "continue"
     else:
-        lines.append("    const int i0 = a0_begin + (int)(t / {}LL);".format(per0))
-        lines.append("    {it} rem = ({it})(t % {p}LL);".format(it='i64' if per0 >= 2 ** 31 else 'int', p=per0))
-        for d in range(1, dim):
-            if d < dim - 1:
-                lines.append("    const int i{d} = (int)(rem / {s}); rem = rem % {s};".format(d=d, s=strides[d]))
-            else:
-                lines.append("    const int i{d} = (int)rem;".format(d=d))
+        lines.append("    if (t >= (i64)(a0_end - a0_begin) * {}LL) return;".format(per0))
+        if dim == 1:
+            lines.append("    const int i0 = a0_begin + (int)t;")
+        else:
+            lines.append("    const int i0 = a0_begin + (int)(t / {}LL);".format(per0))
+            lines.append("    {it} rem = ({it})(t % {p}LL);".format(it='i64' if per0 >= 2 ** 31 else 'int', p=per0))
+            for d in range(1, dim):
+                if d < dim - 1:
+                    lines.append("    const int i{d} = (int)(rem / {s}); rem = rem % {s};".format(d=d, s=strides[d]))
+                else:
+                    lines.append("    const int i{d} = (int)rem;".format(d=d))
     flat = " + ".join("({}){}".format(index_t, "i{}".format(d)) if strides[d] == 1
                       else "({})i{} * {}".format(index_t, d, strides[d]) for d in range(dim))
     lines.append("    const {} idx = {};".format(index_t, flat))
@@ -106,12 +143,14 @@ def generate(program, domain, config=None):
             if program.boundary == 'copy' and program.args[0].ctype != program.out_ctype:
                 halo_value = "({}){}".format(program.out_ctype, halo_value)
             mirror = " if (out_peer) out_peer[idx + peer_shift] = {};".format(halo_value) if domain.is_slab else ""
-            lines.append("    if ({}) {{ out[idx] = {};{} return; }}".format(" || ".join(tests), halo_value, mirror))
+            lines.append("    if ({}) {{ out[idx] = {};{} {}; }}".format(" || ".join(tests), halo_value, mirror, leave))
     lines.append("    {} acc = {};".format(program.out_ctype, ctype_zero(program.out_ctype)))
     lines.extend(emit_statements(program, tap_text, table_text))
     lines.append("    out[idx] = acc;")
     if domain.is_slab:
         lines.append("    if (out_peer) out_peer[idx + peer_shift] = acc;")
+    if vector:
+        lines.append("    }")
     lines.append("}")
     return "\n".join(lines) + "\n"
 
@@ -131,6 +170,14 @@ def direct_config(program, domain):
     The flat kernel is bound by L2 -> L1 traffic (every row is fetched once per tap row that
     touches it: 5 times for the 7-point star); the tiled one fetches 20 rows for 8 points."""
     dim = program.dim
+    if dim == 1 and os.environ.get("STENCIL_CUDA_DIRECT", "tiled") != "flat":
+        grids = [a for a in program.args if a.used_as_grid]
+        vec = 2 if program.out_ctype == 'double' else 4
+        if (program.out_ctype in ('float', 'double') and len(grids) == 1 and grids[0].index == 0
+                and grids[0].ctype == program.out_ctype and program.shape[0] >= 4096
+                and program.npoints < 2 ** 31 - 2 ** 20 and max(program.ghost_depth) <= vec
+                and program.boundary != 'periodic' and not domain.is_slab):
+            return dict(kind='vector1d', V=vec)
     if dim not in (2, 3) or program.shape[-1] < 96 or os.environ.get("STENCIL_CUDA_DIRECT", "tiled") == "flat":
         return dict(kind='flat')
     reach = max(program.ghost_depth)
@@ -285,5 +332,7 @@ def launch_geometry(program, a0_begin, a0_end, config=None):
     for s in program.shape[1:]:
         per0 *= s
     total = (a0_end - a0_begin) * per0
+    if config is not None and config.get('kind') == 'vector1d':
+        total = -(-total // config['V'])                  # a thread owns V consecutive points
     blocks = max(1, (total + BLOCK_THREADS - 1) // BLOCK_THREADS)
     return (blocks, 1, 1), (BLOCK_THREADS, 1, 1)

@@ -42,12 +42,13 @@ SINGLE_FUNCTION = "stencil_rows"
 
 
 def eligible(program, domain):
-    if program.dim != 2 or program.out_ctype != pp.FLOAT:
-        return False, "rank 2 float32 only"
+    if program.dim != 2 or program.out_ctype not in (pp.FLOAT, pp.DOUBLE):
+        return False, "rank 2 float32 / float64 only"
     grids = _grid_args(program)
-    if len(grids) != 1 or grids[0].index != 0 or grids[0].ctype != pp.FLOAT:
-        return False, "exactly one float32 grid argument"
-    if domain.is_slab or domain.is_pitched or program.shape[-1] % 4:
+    if len(grids) != 1 or grids[0].index != 0 or grids[0].ctype != program.out_ctype:
+        return False, "exactly one grid argument, of the output's type"
+    vec = vector_width(program)
+    if domain.is_slab or domain.is_pitched or program.shape[-1] % vec:
         return False, "slab, padded or ragged rows"
     if program.shape[-1] < 256 or program.shape[0] < 16:
         return False, "grid too small"
@@ -58,9 +59,14 @@ def eligible(program, domain):
     if any(isinstance(s, pp.LocalAssign) for s in program.statements):
         return False, "local temporaries"
     lo, hi = program.tap_extent()
-    if max(-lo[1], hi[1]) > 4 or hi[0] - lo[0] > 8:
+    if max(-lo[1], hi[1]) > vec or hi[0] - lo[0] > 8:
         return False, "tap reach"
     return True, "rank-2 stencil"
+
+
+def vector_width(program):
+    """elements a thread owns per row: 16 bytes -- four floats or two doubles"""
+    return 2 if program.out_ctype == pp.DOUBLE else 4
 
 
 def pair_eligible(first, first_domain, second, second_domain):
@@ -70,6 +76,8 @@ def pair_eligible(first, first_domain, second, second_domain):
             return False, why
         if len(program.args) != 1:
             return False, "stencils with table arguments are not fused with other stencils"
+    if first.out_ctype != second.out_ctype:
+        return False, "element types differ"
     if first.shape != second.shape or first.boundary != second.boundary:
         return False, "shape or boundary mode differ"
     return True, "pair of rank-2 stencils"
@@ -99,14 +107,16 @@ def choose_config(program, device_props, second=None, depth=2):
     if depth == 1:
         lo2 = hi2 = 0
     W1, W2 = hi1 - lo1 + 1, hi2 - lo2 + 1
-    PADX = 4 if hx else 0
+    V = vector_width(program)
+    elem = 8 if V == 2 else 4
+    PADX = V if hx else 0
     override = {}
     knob = "STENCIL_CUDA_TEMPORAL_TILE" if depth == 2 else "STENCIL_CUDA_ROWS_TILE"
     for item in filter(None, os.environ.get(knob, "").split(",")):
         key, _, value = item.partition("=")
         override[key.strip()] = int(value)
     window = W1 * W2 // math.gcd(W1, W2)
-    width = 4 + 2 * hx
+    width = (V + 2 * hx) * (elem // 4)          # 32-bit registers of a window row
     # registers: both windows, two accumulator quads, addresses
     best = None
     # measured on B200, 16384^2 (GStencil/s).  Fused, 4-point Jacobi: (4,2) 1491, (8,1) 1477, (4,1) 1373.
@@ -120,7 +130,7 @@ def choose_config(program, device_props, second=None, depth=2):
         order = ((8, 1), (4, 1), (4, 2), (2, 1))
     for NCW, BY in order:
         NCW, BY = override.get("NCW", NCW), override.get("BY", BY)
-        registers = 32 + BY * (W1 + (W2 if depth == 2 else 0)) * width + BY * 8
+        registers = 32 + BY * (W1 + (W2 if depth == 2 else 0)) * width + BY * 2 * V * (elem // 4)
         if registers > 168 and not override:
             continue
         # rows per stage: the window length where that keeps the phase count small
@@ -130,11 +140,11 @@ def choose_config(program, device_props, second=None, depth=2):
         if P > 24 and not override:
             U, S = window, 3
             P = window * (U * S) // math.gcd(window, U * S)
-        pitch = 128 + 2 * PADX
+        pitch = 32 * V + 2 * PADX                                 # elements of a TMA box row
         n_sub = NCW * BY
-        sub_floats = (U * pitch * 4 + 127) // 128 * 32            # every TMA box starts 128-byte aligned
+        sub_floats = (U * pitch * elem + 127) // 128 * (128 // elem)   # elements; every TMA box starts 128-byte aligned
         stage_floats = n_sub * sub_floats
-        smem = S * stage_floats * 4 + 2 * S * 8 + 128
+        smem = S * stage_floats * elem + 2 * S * 8 + 128
         threads = (NCW + 1) * 32
         if smem > device_props.smem_per_block_optin:
             continue
@@ -143,10 +153,10 @@ def choose_config(program, device_props, second=None, depth=2):
         if program.uses_double() or (second is not None and second.uses_double()):
             blocks = min(blocks, 2)                 # double temporaries: leave room, avoid spills
         blocks = override.get("blocks", blocks)
-        out_cols = 128 - (8 if hx and depth == 2 else 0)
-        best = Temporal2dConfig(DEPTH=depth, NCW=NCW, BY=BY, U=U, S=S, HX=hx, PADX=PADX, PITCH=pitch, NSUB=n_sub, W1=W1, W2=W2, P=P,
+        out_cols = 32 * V - (2 * V if hx and depth == 2 else 0)
+        best = Temporal2dConfig(DEPTH=depth, V=V, ELEM=elem, NCW=NCW, BY=BY, U=U, S=S, HX=hx, PADX=PADX, PITCH=pitch, NSUB=n_sub, W1=W1, W2=W2, P=P,
                                 LO1=lo1, HI1=hi1, LO2=lo2, HI2=hi2, STAGE_FLOATS=stage_floats,
-                                STAGE_BYTES=n_sub * U * pitch * 4, SUB_FLOATS=sub_floats, OUT_COLS=out_cols,
+                                STAGE_BYTES=n_sub * U * pitch * elem, SUB_FLOATS=sub_floats, OUT_COLS=out_cols,
                                 TX=n_sub * out_cols, smem_bytes=smem, threads=threads, blocks_per_sm=max(1, blocks))
         break
     if best is None:
@@ -159,7 +169,7 @@ def worthwhile(program, cfg):
     grids that are HBM bound (far larger than L2) and wide enough to fill the sub-tiles."""
     n0, n1 = program.shape
     tiles = -(-n1 // cfg.TX)
-    useful = n1 / float(tiles * cfg.NSUB * 128)
+    useful = n1 / float(tiles * cfg.NSUB * 32 * cfg.V)
     # arithmetic per point: the fused kernel is issue bound for large neighbourhoods (measured on
     # B200, 16384^2, GStencil/s fused vs single sweeps: 4-point Jacobi 1491 vs 773, 3x3 sum 1435 vs
     # 763, 5x5 convolution 615 vs 723)
@@ -187,8 +197,12 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
     j_lo, j_hi = second_domain.interior_lo, second_domain.interior_hi
     two_masks = (tuple(i_lo), tuple(i_hi)) != (tuple(j_lo), tuple(j_hi))
     one_sweep = cfg.DEPTH == 1                     # the row enters the window, the result is stored
-    LANE_PAD = 4 if (HX and not one_sweep) else 0     # the first / last lane of a sub-tile only produce halo
-    cols = list(range(-HX, 4 + HX))                # columns of a window row, relative to the quad
+    V, ELEM = cfg.V, cfg.ELEM                      # elements per thread and row (16 bytes), bytes per element
+    T = program.out_ctype                          # 'float' | 'double'
+    ZERO = "0.0f" if T == pp.FLOAT else "0.0"
+    WIDTH = 32 * V                                 # columns of a warp's sub-tile
+    LANE_PAD = V if (HX and not one_sweep) else 0  # the first / last lane of a sub-tile only produce halo
+    cols = list(range(-HX, V + HX))                # columns of a window row, relative to the thread's first one
     _, const_refs, _, _ = table_plan(program, False)
     _, const_refs2, _, _ = table_plan(second, False)
     const_refs = dict(const_refs, **const_refs2)
@@ -206,18 +220,23 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
     e = _Emitter()
     e.lines.append(PROLOGUE)
     e.lines.append(PTX_HELPERS.replace("@STOP@", os.environ.get("STENCIL_CUDA_STORE_OP", ".cs")))
+    if T == pp.DOUBLE:
+        e.lines.append("""__device__ __forceinline__ void st_global_v2d(double* p, double a, double b) {
+    asm volatile("st.global%s.v2.f64 [%%0], {%%1, %%2};" :: "l"(p), "d"(a), "d"(b) : "memory");
+}""" % os.environ.get("STENCIL_CUDA_STORE_OP", ".cs"))
+    store = "st_global_v4" if T == pp.FLOAT else "st_global_v2d"
     e("// temporal strategy, rank 2: two fused sweeps in registers | grid {} boundary {} | {} warps x {} "
-      "sub-tiles of 128 columns ({} outputs each), U={} rows per stage, ring S={}, windows {}/{}, {} phases".format(
-          program.shape, boundary, NCW, BY, OUTC, U, S, W1, W2, P))
+      "sub-tiles of {} columns ({} outputs each), U={} rows per stage, ring S={}, windows {}/{}, {} phases".format(
+          program.shape, boundary, NCW, BY, WIDTH, OUTC, U, S, W1, W2, P))
     params = ["const {}* __restrict__ a{}".format(arg.ctype, arg.index) for arg in program.args]
-    params += ["const __grid_constant__ TensorMap tm0", "float* __restrict__ out",
-               "float* __restrict__ out_peer", "i64 peer_shift", "int a0_begin", "int a0_end", "int chunk_len"]
+    params += ["const __grid_constant__ TensorMap tm0", "{}* __restrict__ out".format(T),
+               "{}* __restrict__ out_peer".format(T), "i64 peer_shift", "int a0_begin", "int a0_end", "int chunk_len"]
     e('extern "C" __global__ void __launch_bounds__({}, {})'.format(cfg.threads, cfg.blocks_per_sm))
     e("{}({})".format(function, ", ".join(params)))
     e.open("")
     e("extern __shared__ __align__(128) unsigned char smem_raw[];")
-    e("float* const ring = reinterpret_cast<float*>(smem_raw);")
-    e("u64* const bar_full = reinterpret_cast<u64*>(smem_raw + {});".format(S * SF * 4))
+    e("{t}* const ring = reinterpret_cast<{t}*>(smem_raw);".format(t=T))
+    e("u64* const bar_full = reinterpret_cast<u64*>(smem_raw + {});".format(S * SF * ELEM))
     e("u64* const bar_empty = bar_full + {};".format(S))
     e("const int tid = threadIdx.x;")
     e("const int warp = tid >> 5;")
@@ -263,44 +282,55 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
     e()
     # ------------------------------------------------------------------ consumers
     for b in range(BY):
-        e("const int gx{b} = x0 + (warp * {by} + {b}) * {oc} - {pad} + lane * 4;   // first column of quad {b}".format(
-            b=b, by=BY, oc=OUTC, pad=LANE_PAD))
-        e("const float* const src{b} = ring + (warp * {by} + {b}) * {sub} + {px} + lane * 4;".format(
-            b=b, by=BY, sub=SUBF, px=PADX))
+        e("const int gx{b} = x0 + (warp * {by} + {b}) * {oc} - {pad} + lane * {v};   // first column of block {b}".format(
+            b=b, by=BY, oc=OUTC, pad=LANE_PAD, v=V))
+        e("const {t}* const src{b} = ring + (warp * {by} + {b}) * {sub} + {px} + lane * {v};".format(
+            t=T, b=b, by=BY, sub=SUBF, px=PADX, v=V))
         lane_ok = "lane >= 1 && lane <= 30 && " if LANE_PAD else ""
         e("const bool store_ok{b} = {l}gx{b} >= 0 && gx{b} < {n};".format(b=b, l=lane_ok, n=N1))
-        e("float* dst{b} = out + (i64)u_begin * {p} + gx{b};".format(b=b, p=pitch))
+        e("{t}* dst{b} = out + (i64)u_begin * {p} + gx{b};".format(t=T, b=b, p=pitch))
         if clamp and HX:
-            e("const bool x_edge{b} = gx{b} - lane * 4 <= 0 || gx{b} - lane * 4 + {r} > {n};".format(b=b, r=128 + HX, n=N1))
+            e("const bool x_edge{b} = gx{b} - lane * {v} <= 0 || gx{b} - lane * {v} + {r} > {n};".format(
+                b=b, v=V, r=WIDTH + HX, n=N1))
     if not clamp:
         for name, lo_, hi_ in (("halo_mask", i_lo, i_hi),) + ((("halo_mask2", j_lo, j_hi),) if two_masks else ()):
-            e("u32 {} = 0;                   // bit (b*4+j): the point lies in the column halo".format(name))
+            e("u32 {} = 0;                   // bit (b*V+j): the point lies in the column halo".format(name))
             for b in range(BY):
-                for j in range(4):
+                for j in range(V):
                     tests = []
                     if lo_[1] > 0:
                         tests.append("gx{} + {} < {}".format(b, j, lo_[1]))
                     if hi_[1] < N1:
                         tests.append("gx{} + {} >= {}".format(b, j, hi_[1]))
                     if tests:
-                        e("if ({}) {} |= {}u;".format(" || ".join(tests), name, 1 << (b * 4 + j)))
+                        e("if ({}) {} |= {}u;".format(" || ".join(tests), name, 1 << (b * V + j)))
     for (arg, index), ctype in sorted(const_refs.items()):
         e("const {} tc{}_{} = a{}[{}];".format(ctype, arg, index, arg, index))
     names = [in_name(slot, b, c) for slot in range(W1) for b in range(BY) for c in cols]
     if one_sweep:
-        names += [mid_name(0, b, j) for b in range(BY) for j in range(4)]          # the accumulators
+        names += [mid_name(0, b, j) for b in range(BY) for j in range(V)]          # the accumulators
     else:
         names += [mid_name(slot, b, c) for slot in range(W2) for b in range(BY) for c in cols]
     for first in range(0, len(names), 8):
-        e("float {};".format(", ".join(n + " = 0.0f" for n in names[first:first + 8])))
+        e("{} {};".format(T, ", ".join(n + " = " + ZERO for n in names[first:first + 8])))
     counter = [0]
 
     def column_fix(b, names_by_col):
         """'clamp' along a row: cascade the nearest in-grid column outward"""
         for c in sorted((c for c in names_by_col if c < 0), reverse=True):
             e("if (gx{} + ({}) < 0) {} = {};".format(b, c, names_by_col[c], names_by_col[c + 1]))
-        for c in sorted(c for c in names_by_col if c > 3):
+        for c in sorted(c for c in names_by_col if c > V - 1):
             e("if (gx{} + {} > {}) {} = {};".format(b, c, N1 - 1, names_by_col[c], names_by_col[c - 1]))
+
+    def group_loads(needed):
+        """aligned 16-byte / 8-byte / scalar shared-memory loads covering the columns ``needed``"""
+        if V == 4:
+            return _group_loads(needed)
+        loads = []
+        for pair in sorted({c // 2 for c in needed}):
+            used = sorted(c for c in needed if c // 2 == pair)
+            loads.append((2 * pair, 2, used) if len(used) == 2 else (used[0], 1, used))
+        return loads
 
     e("int unit = 0;                        // newest streamed input row, relative to p_first")
     e("u32 par = 0;")
@@ -320,12 +350,12 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
         offset = stage * SF + row * PITCH
         # ---------------- the newest input row enters the window
         for b in range(BY):
-            for first, width, used in _group_loads(set(cols)):
+            for first, width, used in group_loads(set(cols)):
                 if width == 1:
                     e("{} = src{}[{}];".format(in_name(s1, b, used[0]), b, offset + first))
                     continue
                 counter[0] += 1
-                vec = "float4" if width == 4 else "float2"
+                vec = {(4, 4): "float4", (4, 2): "float2", (2, 2): "double2"}[(V, width)]
                 e("const {v} q{n} = *reinterpret_cast<const {v}*>(src{b} + {o});".format(v=vec, n=counter[0], b=b, o=offset + first))
                 e(" ".join("{} = q{}.{};".format(in_name(s1, b, c), counter[0], "xyzw"[c - first]) for c in used))
         if row == U - 1:
@@ -358,10 +388,10 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
         e.open("if (unit >= {})".format(W1 - 1))
         e("const int rm = p_first + unit - ({});".format(HI1))
         for b in range(BY):
-            e(" ".join("{} = 0.0f;".format(mid_name(s2, b, j)) for j in range(4)))
+            e(" ".join("{} = {};".format(mid_name(s2, b, j), ZERO) for j in range(V)))
         for statement in program.statements:
             for b in range(BY):
-                for j in range(4):
+                for j in range(V):
                     def tap_text(tap, b=b, j=j):
                         dr, dc = tap.offset
                         return in_name((s1 + dr - HI1) % W1, b, j + dc)
@@ -378,21 +408,21 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
             e.open("if (rm_halo || halo_mask)")
             e('asm volatile("" ::: "memory");     // keeps this rare case a branch, not selects for everyone')
             for b in range(BY):
-                for j in range(4):
-                    value = in_name((s1 - HI1) % W1, b, j) if copy else "0.0f"
-                    e("if (rm_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * 4 + j), mid_name(s2, b, j), value))
+                for j in range(V):
+                    value = in_name((s1 - HI1) % W1, b, j) if copy else ZERO
+                    e("if (rm_halo || (halo_mask & {}u)) {} = {};".format(1 << (b * V + j), mid_name(s2, b, j), value))
             e.close()
         if one_sweep:
             for b in range(BY):
-                e("if (store_ok{b}) st_global_v4(dst{b}, {v});".format(b=b, v=", ".join(mid_name(s2, b, j) for j in range(4))))
+                e("if (store_ok{b}) {st}(dst{b}, {v});".format(b=b, st=store, v=", ".join(mid_name(s2, b, j) for j in range(V))))
                 e("dst{b} += {p};".format(b=b, p=pitch))
         else:
             # the columns next to the quad come from the neighbouring lanes, once per mid row
             for b in range(BY):
                 for c in cols:
-                    if c < 0 or c > 3:
+                    if c < 0 or c > V - 1:
                         e("{} = __shfl_{}_sync(0xffffffffu, {}, 1);".format(
-                            mid_name(s2, b, c), "up" if c < 0 else "down", mid_name(s2, b, c % 4)))
+                            mid_name(s2, b, c), "up" if c < 0 else "down", mid_name(s2, b, c % V)))
             if clamp and HX:
                 for b in range(BY):
                     e.open("if (x_edge{})".format(b))
@@ -415,12 +445,12 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
 
             # ---------------- sweep 2: output row zo = rm - HI2
             e.open("if (unit >= {})".format((W1 - 1) + (W2 - 1)))
-            acc = [["acc{}_{}".format(b, j) for j in range(4)] for b in range(BY)]
+            acc = [["acc{}_{}".format(b, j) for j in range(V)] for b in range(BY)]
             for b in range(BY):
-                e("float {};".format(", ".join(n + " = 0.0f" for n in acc[b])))
+                e("{} {};".format(T, ", ".join(n + " = " + ZERO for n in acc[b])))
             for statement in second.statements:
                 for b in range(BY):
-                    for j in range(4):
+                    for j in range(V):
                         def tap_text(tap, b=b, j=j):
                             dr, dc = tap.offset
                             return mid_name((s2 + dr - HI2) % W2, b, j + dc)
@@ -439,12 +469,12 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
                 e.open("if (zo_halo || {})".format(mask2))
                 e('asm volatile("" ::: "memory");     // keeps this rare case a branch, not selects for everyone')
                 for b in range(BY):
-                    for j in range(4):
-                        value = mid_name((s2 - HI2) % W2, b, j) if copy else "0.0f"
-                        e("if (zo_halo || ({} & {}u)) {} = {};".format(mask2, 1 << (b * 4 + j), acc[b][j], value))
+                    for j in range(V):
+                        value = mid_name((s2 - HI2) % W2, b, j) if copy else ZERO
+                        e("if (zo_halo || ({} & {}u)) {} = {};".format(mask2, 1 << (b * V + j), acc[b][j], value))
                 e.close()
             for b in range(BY):
-                e("if (store_ok{b}) st_global_v4(dst{b}, {v});".format(b=b, v=", ".join(acc[b])))
+                e("if (store_ok{b}) {st}(dst{b}, {v});".format(b=b, st=store, v=", ".join(acc[b])))
                 e("dst{b} += {p};".format(b=b, p=pitch))
             e.close()   # sweep 2
         e.close()   # sweep 1
@@ -469,7 +499,8 @@ def make_plan(program, domain, device_props, options, second=None, second_domain
     cfg = choose_config(program, device_props, second)
     source = generate(program, domain, cfg, second=second, second_domain=second_domain)
     n0, n1 = program.shape
-    specs = [TensorMapSpec(0, (n1, n0), (domain.row_pitch * 4,), (cfg.PITCH, cfg.U), tag="temporal-rows")]
+    specs = [TensorMapSpec(0, (n1, n0), (domain.row_pitch * cfg.ELEM,), (cfg.PITCH, cfg.U),
+                           dtype_code=1 if cfg.ELEM == 8 else 0, tag="temporal-rows")]
     tiles = -(-n1 // cfg.TX)
     slots = device_props.sm_count * cfg.blocks_per_sm
     warmup = (cfg.W1 - 1) + (cfg.W2 - 1)
@@ -502,7 +533,8 @@ def single_applicable(program, domain):
     if not ok:
         return False
     lo, hi = program.tap_extent()
-    width = 4 + 2 * max(-lo[1], hi[1])
+    vec = vector_width(program)
+    width = (vec + 2 * max(-lo[1], hi[1])) * (4 // vec)          # 32-bit registers of a window row
     return 32 + (hi[0] - lo[0] + 1) * width + 8 <= 168
 
 
@@ -513,7 +545,8 @@ def make_single_plan(program, domain, device_props, options):
     cfg = choose_config(program, device_props, depth=1)
     source = generate(program, domain, cfg, function=SINGLE_FUNCTION)
     n0, n1 = program.shape
-    specs = [TensorMapSpec(0, (n1, n0), (domain.row_pitch * 4,), (cfg.PITCH, cfg.U), tag="rows")]
+    specs = [TensorMapSpec(0, (n1, n0), (domain.row_pitch * cfg.ELEM,), (cfg.PITCH, cfg.U),
+                           dtype_code=1 if cfg.ELEM == 8 else 0, tag="rows")]
     tiles = -(-n1 // cfg.TX)
     slots = device_props.sm_count * cfg.blocks_per_sm
     floors = (max(4 * cfg.U, 64), 2 * cfg.U)

@@ -44,19 +44,23 @@ def plan(program, domain, device_props=None, forced_strategy=None, options=()):
     reason = "forced" if forced_strategy else None
     if domain.is_pitched:
         strategy = 'stream'              # padded rows exist only for the TMA kernels (iterate())
+    from . import codegen_stream
+    rows_kernel = False
+    if program.dim == 2 and not codegen_stream.wants_plane_embedding(program, domain):
+        from . import codegen_temporal2d
+        rows_kernel = codegen_temporal2d.single_applicable(program, domain)
     if strategy is None:
-        from . import codegen_stream
         ok, reason = codegen_stream.applicable(program, domain, device_props)
+        if not ok and rows_kernel and program.npoints >= (1 << 20):
+            ok, reason = True, "rank-2 {} grid on the row pipeline".format(program.out_ctype)   # float64
         strategy = 'stream' if ok else 'direct'
     if strategy == 'stream':
-        from . import codegen_stream
+        if rows_kernel:
+            # rank-2 single sweeps: the row pipeline with compile-time ring indices (float32 / float64)
+            return codegen_temporal2d.make_single_plan(program, domain, device_props, options)
         ok, why = codegen_stream.applicable(program, domain, device_props, forced=True)
         if not ok:
             raise StencilException("strategy 'stream' cannot handle this stencil: " + why)
-        if program.dim == 2 and not codegen_stream.wants_plane_embedding(program, domain):
-            from . import codegen_temporal2d
-            if codegen_temporal2d.single_applicable(program, domain):
-                return codegen_temporal2d.make_single_plan(program, domain, device_props, options)
         return codegen_stream.make_plan(program, domain, device_props, options)
     if strategy != 'direct':
         raise StencilException("unknown strategy '{}'".format(strategy))

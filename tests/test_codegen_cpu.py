@@ -310,5 +310,6 @@ def test_point_kernel_tiles_share_tap_loads():
     assert double.notes['config'] == {'kind': 'tiled', 'RY': 4, 'RZ': 2}      # doubles count twice
     runtime.compile_source(double.source, "tiled64.cu", double.options)
     assert make_plan(LaplacianKernel(), [((64, 96, 64), numpy.float32)], 'direct').notes['config']['kind'] == 'flat'
-    assert make_plan(Stencil1d(), [((4096,), numpy.float32)], 'direct').notes['config']['kind'] == 'flat'
+    assert make_plan(Stencil1d(), [((1000,), numpy.float32)], 'direct').notes['config']['kind'] == 'flat'
+    assert make_plan(Stencil1d(), [((4096,), numpy.float32)], 'direct').notes['config'] == {'kind': 'vector1d', 'V': 4}
     assert codegen_direct.direct_config(plan.program, plan.domain)['kind'] == 'tiled'

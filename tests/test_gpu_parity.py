@@ -481,3 +481,65 @@ def test_rank2_pairs_fuse_into_one_launch(monkeypatch):
         three = fuse(first, second, Jacobi(boundary_handling=mode))
         expected = oracle_output(Jacobi(backend='python', boundary_handling=mode), expected)
         assert_bit_identical(three(grid), expected)
+
+
+@pytest.mark.parametrize("mode", ["clamp", "zero", "copy"])
+def test_float64_rank2_grids_on_the_row_pipeline(mode, monkeypatch):
+    """float64 rank-2 grids (the reference's known-answer tests use float64,
+    test/test_boundary_handling.py:56) stream through TMA like float32 ones: two doubles per
+    thread, single sweeps (stencil_rows) and fused pairs (stencil_temporal2_rows), same bits as
+    the oracle."""
+    from cases import CONV5, OddWeights
+    from stencil_code_b200.library.convolution import ConvolutionFilter
+    from stencil_code_b200.library.diagnostic_stencil import DiagnosticStencil
+    from stencil_code_b200.library.jacobi_stencil import Jacobi
+    monkeypatch.setenv("STENCIL_CUDA_TEMPORAL", "force")
+    monkeypatch.setenv("STENCIL_CUDA_STRATEGY", "stream")
+    makes = {"diagnostic": lambda backend: DiagnosticStencil(backend=backend, boundary_handling=mode),
+             "jacobi2d": lambda backend: Jacobi(backend=backend, boundary_handling=mode),
+             "odd_weights": lambda backend: OddWeights(backend=backend, boundary_handling=mode),
+             "conv5": lambda backend: ConvolutionFilter(CONV5 / 64.0, backend=backend, boundary_handling=mode)}
+    for name, make in makes.items():
+        for shape in ((40, 256), (37, 390), (130, 1024), (19, 2050)):
+            grid = numpy.random.RandomState(43).random_sample(shape) * 0.01
+            assert grid.dtype == numpy.float64
+            stencil, python_side = make('cuda'), make('python')
+            hidden = (stencil.coefficients,) if name == "conv5" else ()
+            concrete = stencil.specializer.specialize((grid,) + hidden)
+            assert concrete.plan.function == "stencil_rows", (name, shape, concrete.plan.function)
+            expected = oracle_output(python_side, grid)
+            actual = stencil(grid)
+            assert actual.dtype == numpy.float64
+            assert_bit_identical(actual, expected)
+            fused = concrete.temporal()
+            assert fused is not None and fused[0].function == "stencil_temporal2_rows"
+            for sweeps in (2, 3):
+                expected = oracle_output(python_side, expected)
+                assert_bit_identical(stencil.iterate(grid, sweeps), expected)
+    # the planner takes the row pipeline for large float64 rank-2 grids on its own
+    monkeypatch.delenv("STENCIL_CUDA_STRATEGY")
+    big = numpy.random.RandomState(44).random_sample((1024, 2048))
+    stencil = makes["diagnostic"]('cuda')
+    assert stencil.specializer.specialize((big,)).plan.function == "stencil_rows"
+    assert_bit_identical(stencil(big), oracle_output(makes["diagnostic"]('python'), big, variant='c_parallel'))
+
+
+@pytest.mark.parametrize("dtype", [numpy.float32, numpy.float64])
+def test_rank1_grids_on_the_vector_kernel(dtype):
+    """Large rank-1 grids (reference test/test_boundary_handling.py:145-151 is the 24-point case):
+    a thread owns 16 bytes of consecutive points; edge groups, unaligned views and tails run the
+    one-point code.  All modes, lengths that are and are not multiples of the vector, a torch view
+    that starts 4 bytes into an allocation."""
+    import torch
+    from cases import Stencil1d
+    for mode in ("clamp", "zero", "copy"):
+        for length in (4096, 5000, 65537, 1 << 20):
+            grid = (numpy.random.RandomState(47).random_sample((length,)) * 1000).astype(dtype)
+            stencil = Stencil1d(backend='cuda', boundary_handling=mode)
+            concrete = stencil.specializer.specialize((grid,))
+            assert concrete.plan.notes['config']['kind'] == 'vector1d'
+            expected = oracle_output(Stencil1d(backend='python', boundary_handling=mode), grid)
+            assert_bit_identical(stencil(grid), expected)
+        whole = torch.from_numpy(numpy.concatenate([numpy.zeros(1, dtype), grid])).cuda()
+        view = whole[1:]                                    # contiguous, but not 16-byte aligned
+        assert_bit_identical(stencil(view).cpu().numpy(), expected)
