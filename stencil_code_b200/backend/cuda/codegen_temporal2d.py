@@ -205,7 +205,8 @@ def generate(program, domain, cfg, second=None, second_domain=None, function=FUN
     cols = list(range(-HX, V + HX))                # columns of a window row, relative to the thread's first one
     _, const_refs, _, _ = table_plan(program, False)
     _, const_refs2, _, _ = table_plan(second, False)
-    const_refs = dict(const_refs, **const_refs2)
+    const_refs = dict(const_refs)
+    const_refs.update(const_refs2)               # keys are (argument, index) pairs
     pitch = domain.row_pitch
 
     def in_name(slot, b, col):
