@@ -727,6 +727,9 @@ def make_plan(program, domain, device_props, options, second=None, second_domain
     def geometry(a0_begin, a0_end):
         n_units = a0_end - a0_begin
         chunks = plan_chunks(n_units, tiles_x * tiles_y, slots, 5, 32)
+        forced = int(os.environ.get("STENCIL_CUDA_TEMPORAL_CHUNKS", "0"))        # tuning knob
+        if forced:
+            chunks = max(1, min(forced, n_units // 4))
         chunk_len = -(-n_units // chunks)
         chunks = -(-n_units // chunk_len)
         launch = Launch((tiles_x, tiles_y, chunks), (cfg.threads, 1, 1), cfg.smem_bytes)

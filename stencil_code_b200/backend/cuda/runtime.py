@@ -658,7 +658,8 @@ class ConcreteCudaStencil(object):
         nbytes = (hi - lo) * plane_bytes
         chunks = 1
         if pipelined and nbytes >= self.PIPELINE_MIN_BYTES:
-            chunks = max(1, min(64, nbytes // self.PIPELINE_CHUNK_BYTES, (hi - lo) // max(1, 4 * ghost)))
+            chunk_bytes = int(os.environ.get("STENCIL_CUDA_PIPELINE_CHUNK_MB", "0")) << 20 or self.PIPELINE_CHUNK_BYTES
+            chunks = max(1, min(64, nbytes // chunk_bytes, (hi - lo) // max(1, 4 * ghost)))
 
         def copy_in_planes(begin, end, stream):
             begin, end = max(begin, in_lo), min(end, in_hi)
