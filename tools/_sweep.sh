@@ -1,10 +1,5 @@
-T="timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-{
-$T --master-port 29521 tools/probe_slab.py 100
-STENCIL_CUDA_PDL=0 $T --master-port 29522 tools/probe_slab.py 100
-STENCIL_CUDA_TEMPORAL_CHUNKS=2 $T --master-port 29523 tools/probe_slab.py 100
-STENCIL_CUDA_TEMPORAL_CHUNKS=3 $T --master-port 29524 tools/probe_slab.py 100
-STENCIL_CUDA_TEMPORAL_CHUNKS=6 $T --master-port 29525 tools/probe_slab.py 100
-STENCIL_CUDA_TEMPORAL_TILE="MY=32,BY=2,NCW=16,prefetch=4" $T --master-port 29526 tools/probe_slab.py 100
-STENCIL_CUDA_STEP_KERNEL=0 $T --master-port 29527 tools/probe_slab.py 100
-} 2>&1 | grep "C5 on" | cut -c1-200
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -n 2 gpurun_out/r2_smoke.log
+(time timeout 300 python bench.py --steps 20 --warmup 5) > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; tail -n 4 gpurun_out/r2_bench_final.err
+timeout 120 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_bench_ref_final.json 2> gpurun_out/r2_bench_ref_final.err
+timeout 100 python bench.py --workload laplacian512 --quick --no-cpu --steps 100 > gpurun_out/r2_bench_lap.json 2> gpurun_out/r2_bench_lap.err; tail -c 200 gpurun_out/r2_bench_lap.err
+timeout 600 python -m pytest tests -m gpu -x -q --durations=5 > gpurun_out/r2_gpu_tests_final.log 2>&1; tail -n 10 gpurun_out/r2_gpu_tests_final.log
