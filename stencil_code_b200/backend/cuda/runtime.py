@@ -243,6 +243,7 @@ class Device(object):
         self.d2h_stream = self._new_stream()
         self._free_device = {}       # nbytes -> [ptr]
         self._free_pinned = {}       # nbytes -> [ptr]
+        self._pool_lock = threading.RLock()   # finalizers of dropped buffers may run on any thread
         self._events = []
         self._utils = None
 
@@ -295,9 +296,11 @@ class Device(object):
     # -- device memory (size-keyed free lists: a call's buffers are reused by the next call)
     def alloc(self, nbytes):
         nbytes = max(256, (int(nbytes) + 255) // 256 * 256)
-        bucket = self._free_device.get(nbytes)
-        if bucket:
-            return DeviceBuffer(self, bucket.pop(), nbytes)
+        with self._pool_lock:
+            bucket = self._free_device.get(nbytes)
+            pooled = bucket.pop() if bucket else None
+        if pooled is not None:
+            return DeviceBuffer(self, pooled, nbytes)
         pointer = ctypes.c_void_p()
         code = load_library().sc_malloc(ctypes.byref(pointer), nbytes)
         if code != 0:
@@ -306,17 +309,19 @@ class Device(object):
         return DeviceBuffer(self, pointer.value, nbytes)
 
     def _release(self, pointer, nbytes):
-        self._free_device.setdefault(nbytes, []).append(pointer)
+        with self._pool_lock:
+            self._free_device.setdefault(nbytes, []).append(pointer)
 
     def trim(self):
         """Return every cached device / pinned block to the driver."""
         library = load_library()
-        for bucket in self._free_device.values():
-            while bucket:
-                library.sc_free(ctypes.c_void_p(bucket.pop()))
-        for bucket in self._free_pinned.values():
-            while bucket:
-                library.sc_host_free(ctypes.c_void_p(bucket.pop()))
+        with self._pool_lock:
+            for bucket in self._free_device.values():
+                while bucket:
+                    library.sc_free(ctypes.c_void_p(bucket.pop()))
+            for bucket in self._free_pinned.values():
+                while bucket:
+                    library.sc_host_free(ctypes.c_void_p(bucket.pop()))
 
     # -- pinned host memory
     def pinned_empty(self, shape, dtype):
@@ -324,10 +329,10 @@ class Device(object):
         dtype = numpy.dtype(dtype)
         count = int(numpy.prod(shape, dtype=numpy.int64)) if len(shape) else 1
         nbytes = max(4096, (count * dtype.itemsize + 4095) // 4096 * 4096)
-        bucket = self._free_pinned.get(nbytes)
-        if bucket:
-            pointer = bucket.pop()
-        else:
+        with self._pool_lock:
+            bucket = self._free_pinned.get(nbytes)
+            pointer = bucket.pop() if bucket else None
+        if pointer is None:
             raw = ctypes.c_void_p()
             check(load_library().sc_host_alloc(ctypes.byref(raw), nbytes), "pinned allocation")
             pointer = raw.value
@@ -343,16 +348,17 @@ class Device(object):
         The idle pool is bounded: beyond PINNED_POOL_LIMIT older idle blocks go back to the
         driver, so that at most the limit -- or one single larger block -- stays page-locked."""
         library = load_library()
-        pool = self._free_pinned
-        idle = sum(size * len(bucket) for size, bucket in pool.items())
-        for size in list(pool):
-            bucket = pool[size]
-            while bucket and idle + nbytes > self.PINNED_POOL_LIMIT:
-                library.sc_host_free(ctypes.c_void_p(bucket.pop(0)))
-                idle -= size
-            if not bucket:
-                del pool[size]
-        pool.setdefault(nbytes, []).append(pointer)
+        with self._pool_lock:
+            pool = self._free_pinned
+            idle = sum(size * len(bucket) for size, bucket in pool.items())
+            for size in list(pool):
+                bucket = pool[size]
+                while bucket and idle + nbytes > self.PINNED_POOL_LIMIT:
+                    library.sc_host_free(ctypes.c_void_p(bucket.pop(0)))
+                    idle -= size
+                if not bucket:
+                    del pool[size]
+            pool.setdefault(nbytes, []).append(pointer)
 
     # -- helper kernels (csrc/device_utils.cu)
     def utils(self):
