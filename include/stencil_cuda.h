@@ -130,6 +130,18 @@ int         sc_launch_pingpong(sc_module* module, const char* function,
  * griddepcontrol.wait before they touch memory the preceding launch writes or reads            */
 #define SC_LAUNCH_PROGRAMMATIC 1u
 
+/* A launch prepared once and repeated: function lookup, shared-memory opt-in and launch
+ * configuration are resolved by sc_prepare_launch; sc_launch_prepared is then one call with two
+ * arguments (the binding's per-call cost matters for stencils that run in a few microseconds:
+ * the reference's 1024 x 1024 timing case).  `args` must stay valid until sc_prepared_free; the
+ * parameter values are read at every launch.                                                  */
+typedef struct sc_prepared sc_prepared;
+int         sc_prepare_launch(sc_module* module, const char* function,
+                              const uint32_t grid[3], const uint32_t block[3], const uint32_t cluster[3],
+                              uint32_t dynamic_smem, void** args, sc_prepared** prepared);
+int         sc_launch_prepared(sc_prepared* prepared, void* stream);
+int         sc_prepared_free(sc_prepared* prepared);
+
 /* As sc_launch_pingpong, for kernels that take the number of the step they perform as a 32-bit
  * parameter: launch i receives `first_step + i` in parameter `step_arg` (an index into the args
  * arrays; the pointed-to uint32_t of both blocks is overwritten).  Used by the slab-decomposed

@@ -69,6 +69,9 @@ SYMBOLS = {
                                 ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), _I]),
     "sc_launch": (_I, [_VP, ctypes.c_char_p, _U32x3, _U32x3, _U32x3, ctypes.c_uint32, _VP, _PVP]),
     "sc_launch_pingpong": (_I, [_VP, ctypes.c_char_p, _U32x3, _U32x3, ctypes.c_uint32, _VP, _PVP, _PVP, _I, ctypes.c_uint32]),
+    "sc_prepare_launch": (_I, [_VP, ctypes.c_char_p, _U32x3, _U32x3, _U32x3, ctypes.c_uint32, _PVP, _PVP]),
+    "sc_launch_prepared": (_I, [_VP, _VP]),
+    "sc_prepared_free": (_I, [_VP]),
     "sc_launch_steps": (_I, [_VP, ctypes.c_char_p, _U32x3, _U32x3, ctypes.c_uint32, _VP, _PVP, _PVP, _I, ctypes.c_uint32,
                              _I, ctypes.c_uint32]),
     "sc_stream_create": (_I, [_PVP]),
@@ -412,6 +415,23 @@ def launch(module, function, launch_cfg, args, stream):
                             launch_cfg.smem, stream, pointers), "launch of " + function)
 
 
+class _PreparedLaunch(object):
+    """A launch resolved once (``sc_prepare_launch``): kernel handle, shared-memory opt-in, geometry
+    and the argument block; freed with the cache entry that holds it."""
+    def __init__(self, module, name, grid, block, cluster, smem, pointers):
+        self.handle = ctypes.c_void_p()
+        self._keep = (module, pointers, grid, block, cluster)
+        check(load_library().sc_prepare_launch(module.handle, name, grid, block, cluster, smem, pointers,
+                                               ctypes.byref(self.handle)), "preparing a launch")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                load_library().sc_prepared_free(self.handle)
+        except Exception:
+            pass
+
+
 # ---- the concrete callable ----------------------------------------------------------------------
 def _is_torch_tensor(obj):
     return hasattr(obj, "data_ptr") and hasattr(obj, "is_cuda")
@@ -440,6 +460,7 @@ class ConcreteCudaStencil(object):
         self._twin = None                # specialisation over padded rows (see _pitched_twin)
         self._pairs = {}                 # id(other concrete stencil) -> (other, fused (plan, module) or None)
         self._sc_launch = load_library().sc_launch
+        self._sc_launch_prepared = load_library().sc_launch_prepared
         self.last_duration = None        # seconds of the last call when STENCIL_CUDA_TIMING=1
 
     # -- argument checks (the reference's ndpointer argtypes raise TypeError on mismatch)
@@ -509,19 +530,19 @@ class ConcreteCudaStencil(object):
             function = plan.function
             if not peer_pointer and getattr(plan, 'function_no_peer', None):
                 function = plan.function_no_peer
-            prepared = (values, pointers, (ctypes.c_uint32 * 3)(*geometry.grid),
-                        (ctypes.c_uint32 * 3)(*geometry.block), (ctypes.c_uint32 * 3)(*geometry.cluster),
-                        geometry.smem, function.encode())
+            grid3 = (ctypes.c_uint32 * 3)(*geometry.grid)
+            block3 = (ctypes.c_uint32 * 3)(*geometry.block)
+            cluster3 = (ctypes.c_uint32 * 3)(*geometry.cluster)
+            prepared = (values, pointers, grid3, block3, cluster3, geometry.smem, function.encode(),
+                        _PreparedLaunch(module, function.encode(), grid3, block3, cluster3, geometry.smem, pointers))
             while len(self._launches) >= 1024:
                 self._launches.pop(next(iter(self._launches)))
-        else:
-            del self._launches[key]
-        self._launches[key] = prepared
+            self._launches[key] = prepared
         if prepare_only:
             return prepared
-        _, pointers, grid, block, cluster, smem, name = prepared
-        code = self._sc_launch(module.handle, name, grid, block, cluster, smem,
-                               self.device.stream if stream is None else stream, pointers)
+        # one C call with two arguments: function, geometry and argument block were resolved when the
+        # launch was prepared (the per-call cost of the binding is what bounds microsecond stencils)
+        code = self._sc_launch_prepared(prepared[7].handle, self.device.stream if stream is None else stream)
         if code != 0:
             check(code, "launch of " + plan.function)
 
@@ -870,7 +891,7 @@ class ConcreteCudaStencil(object):
                                     prepare_only=True)
             if even is None or launches <= 0:
                 return
-            _, pointers, grid, block, _, smem, name = even
+            _, pointers, grid, block, _, smem, name = even[:7]
             check(load_library().sc_launch_pingpong(module.handle, name, grid, block, smem, stream,
                                                     pointers, odd[1], launches, programmatic), "iterated launch")
         if fused is not None and remaining >= 2:

@@ -560,6 +560,58 @@ int sc_launch_pingpong(sc_module* module, const char* function, const uint32_t g
     return SC_OK;
 }
 
+struct sc_prepared {
+    CUfunction fn;
+    CUlaunchConfig config;
+    CUlaunchAttribute attribute;
+    void** args;
+    int device;
+};
+
+int sc_prepare_launch(sc_module* module, const char* function, const uint32_t grid[3],
+                      const uint32_t block[3], const uint32_t cluster[3], uint32_t dynamic_smem,
+                      void** args, sc_prepared** prepared) {
+    if (!module || !function || !grid || !block || !prepared) return fail(SC_EINVAL, "NULL argument");
+    CUfunction fn;
+    int rc = get_function(module, function, &fn);
+    if (rc != SC_OK) return rc;
+    rc = optin_smem(module, function, fn, dynamic_smem);
+    if (rc != SC_OK) return rc;
+    sc_prepared* p = new sc_prepared();
+    p->fn = fn;
+    p->args = args;
+    p->device = current_device_index();
+    memset(&p->config, 0, sizeof p->config);
+    p->config.gridDimX = grid[0]; p->config.gridDimY = grid[1]; p->config.gridDimZ = grid[2];
+    p->config.blockDimX = block[0]; p->config.blockDimY = block[1]; p->config.blockDimZ = block[2];
+    p->config.sharedMemBytes = dynamic_smem;
+    memset(&p->attribute, 0, sizeof p->attribute);
+    if (cluster && (cluster[0] > 1 || cluster[1] > 1 || cluster[2] > 1)) {
+        p->attribute.id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
+        p->attribute.value.clusterDim.x = cluster[0];
+        p->attribute.value.clusterDim.y = cluster[1];
+        p->attribute.value.clusterDim.z = cluster[2];
+        p->config.attrs = &p->attribute;
+        p->config.numAttrs = 1;
+    }
+    *prepared = p;
+    return SC_OK;
+}
+
+int sc_launch_prepared(sc_prepared* prepared, void* stream) {
+    if (!prepared) return fail(SC_EINVAL, "prepared is NULL");
+    CUlaunchConfig config = prepared->config;           // a copy: the same prepared launch may be used on several streams
+    config.hStream = reinterpret_cast<CUstream>(stream);
+    CUresult cu = g_drv.cuLaunchKernelEx_(&config, prepared->fn, prepared->args, nullptr);
+    if (cu != CUDA_SUCCESS) return cuda_fail(cu, "cuLaunchKernelEx(prepared)");
+    return SC_OK;
+}
+
+int sc_prepared_free(sc_prepared* prepared) {
+    delete prepared;
+    return SC_OK;
+}
+
 int sc_launch_steps(sc_module* module, const char* function, const uint32_t grid[3],
                     const uint32_t block[3], uint32_t dynamic_smem, void* stream,
                     void** args_even, void** args_odd, int count, uint32_t flags,
