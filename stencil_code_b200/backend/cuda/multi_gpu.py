@@ -75,6 +75,13 @@ class SlabDecomposition(object):
         bottom = (max(hi - self.g, top[1]), hi) if self.open_hi else (hi, hi)
         return top, (top[1], bottom[0]), bottom
 
+    def host_window(self):
+        """Global axis-0 plane range [lo, hi) this rank needs from the host for one sweep: its real
+        planes plus the ghost planes that border another slab."""
+        lo = max(0, self.start - self.first_real)
+        hi = min(self.global_shape[0], self.stop + (self.g if self.ghosted else 0))
+        return lo, hi
+
     def sends(self):
         """[(neighbour rank, local source range, neighbour's local destination range)]"""
         plan = []
@@ -287,10 +294,7 @@ class SlabStencil(object):
     def host_window(self):
         """Global axis-0 plane range [lo, hi) this rank needs from the host: its real planes plus
         the ghost planes that border another slab."""
-        slab = self.slab
-        lo = max(0, slab.start - slab.first_real)
-        hi = min(slab.global_shape[0], slab.stop + (slab.g if slab.ghosted else 0))
-        return lo, hi
+        return self.slab.host_window()
 
     def apply_host(self, window, out=None):
         """ONE sweep, host memory to host memory, on this rank's slab: ``window`` holds the global

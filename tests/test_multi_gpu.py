@@ -143,3 +143,93 @@ def test_step_kernel_geometry_covers_the_slab():
     # the three entry points cross-compile for sm_100a (with the griddepcontrol instructions in)
     module = runtime.compile_source(fused.source, "step_check.cu", list(fused.options) + ["-DSC_PDL"])
     assert module.cubin()[:4] == b"\x7fELF"
+
+
+def test_host_windows_cover_what_a_sweep_reads():
+    """apply_host: the planes a rank takes from the host are its real planes plus the ghost planes
+    towards each neighbour, clipped to the grid; neighbouring windows overlap by 2 g planes."""
+    for world, ghost in ((1, None), (2, None), (4, 2), (8, 2)):
+        parts = [SlabDecomposition((2048, 8, 8), 1, world, r, ghost_planes=ghost) for r in range(world)]
+        for r, part in enumerate(parts):
+            lo, hi = part.host_window()
+            g = part.g if world > 1 else 0
+            assert lo == max(0, part.start - g) and hi == min(2048, part.stop + g)
+            assert hi - lo <= part.local_shape[0]
+            local_lo = lo - (part.start - part.first_real)          # where the window starts in the local array
+            assert local_lo == (0 if r > 0 or world == 1 else part.first_real)
+            if r + 1 < world:
+                assert hi - parts[r + 1].host_window()[0] == 2 * g
+
+
+def test_pipelined_host_sweep_copies_and_sweeps_every_plane_once():
+    """ConcreteCudaStencil.sweep_host with a recording stand-in for the C ABI: whatever the chunking,
+    every input plane of the window is copied to the device exactly once, the launches tile the
+    sweep range in order, every output plane is copied back exactly once, and no chunk is swept
+    before the planes it reads (its own and the first ghost planes of the next chunk) were enqueued."""
+    import numpy
+    from stencil_code_b200.backend.cuda import runtime
+
+    class Recorder(object):
+        def __init__(self):
+            self.log = []
+
+        def __getattr__(self, name):
+            def call(*args):
+                self.log.append((name,) + tuple(a.value if hasattr(a, "value") else a for a in args))
+                return 0
+            return call
+
+    class FakeDevice(object):
+        stream, h2d_stream, d2h_stream = "compute", "h2d", "d2h"
+
+        def __init__(self):
+            self.events = 0
+
+        def event(self):
+            self.events += 1
+            return "event{}".format(self.events)
+
+        def recycle_event(self, event):
+            pass
+
+        def synchronize(self, stream=None):
+            pass
+
+    class Program(object):
+        shape, out_dtype_size, ghost_depth = (300, 512, 512), 4, (2, 1, 1)
+
+    recorder = Recorder()
+    original = runtime.load_library
+    runtime.load_library = lambda: recorder
+    try:
+        stencil = object.__new__(runtime.ConcreteCudaStencil)
+        stencil.device, stencil.program = FakeDevice(), Program()
+        launches = []
+        stencil.launch = lambda pointers, out, begin, end, stream=None: (
+            launches.append((begin, end)), recorder.log.append(("launch", begin, end)))
+        plane = 512 * 512 * 4
+        # a slab window: local planes 0..300 come from the host, planes 2..298 are swept
+        stencil.sweep_host(1 << 40, (0, 300), [1 << 30], 1 << 31, (1 << 41) - 2 * plane, (2, 298))
+    finally:
+        runtime.load_library = original
+    copied_in = numpy.zeros(300, int)
+    copied_out = numpy.zeros(300, int)
+    landed = numpy.zeros(300, bool)
+    for entry in recorder.log:
+        if entry[0] == "sc_memcpy_h2d_async":
+            first = (entry[1] - (1 << 30)) // plane
+            count = entry[3] // plane
+            assert (entry[2] - (1 << 40)) // plane == first            # host offset matches the device offset
+            copied_in[first:first + count] += 1
+            landed[first:first + count] = True
+        elif entry[0] == "launch":
+            begin, end = entry[1], entry[2]
+            assert landed[max(0, begin - 2):min(300, end + 2)].all(), "swept before its input was enqueued"
+        elif entry[0] == "sc_memcpy_d2h_async":
+            first = (entry[2] - (1 << 31)) // plane
+            assert (entry[1] - ((1 << 41) - 2 * plane)) // plane == first
+            copied_out[first:first + entry[3] // plane] += 1
+    assert (copied_in == 1).all()
+    assert (copied_out[2:298] == 1).all() and copied_out[:2].sum() == 0 and copied_out[298:].sum() == 0
+    assert launches[0][0] == 2 and launches[-1][1] == 298 and len(launches) > 4
+    assert all(a[1] == b[0] for a, b in zip(launches, launches[1:]))
